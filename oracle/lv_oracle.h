@@ -1,0 +1,80 @@
+/*
+ * lv_oracle.h -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C restatement of the reference's per-frame hot path (wonsang/LiveVideo):
+ *   - YUV 4:2:0 -> 24-bit RGB conversion: class ColorSpaceConversions, /root/reference/Convert.h:19-31,
+ *     code only as object code in /root/reference/cscc.lib (Convert.obj .text+0x000 ctor tables,
+ *     .text+0x350 YV12_to_RGB24).
+ *   - background/frame difference: IsNearlyZero, /root/reference/lib/JM/image.h:22 (= MainDlg.h:9),
+ *     loops lib/JM/image.c:4791-4804 and MainDlg.cpp:804-810.
+ *   - 16x16 macroblock grid and "block is ON" scan: lib/JM/image.c:4677-4679, 4981, 5143-5150.
+ *   - previous-frame retention: lib/JM/image.c:1553-1561 (alloc 556-570, calloc => zero initial state).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * link or call this library.  The product (livevideo_b200/csrc) never does.
+ *
+ * Parity status: the conversion is PINNED -- tests check it against the reference's original
+ * object code (oracle/_ref/oracle32, built by oracle/ref32/build_ref.py) on all 2^24 (Y,U,V)
+ * triples and against the golden digests of SURVEY.md section 8(c).  The difference/macroblock
+ * part has no upstream test or binary: "parity unpinned" by the reference, pinned by the cited
+ * source lines only.
+ */
+#ifndef LV_ORACLE_H
+#define LV_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- conversion (Convert.obj) ------------------------------------------------------------- */
+void lvo_init_tables(void);                                   /* ctor, .text+0x110..0x1c1 */
+void lvo_yv12_to_rgb24(const uint8_t *src_y, const uint8_t *src_u, const uint8_t *src_v,
+                       uint8_t *dst, int width, int height);  /* .text+0x350..0x73f */
+void lvo_yuv_to_bgr_px(int y, int u, int v, uint8_t bgr[3]);  /* one pixel through the tables */
+/* textbook >>16 form -- NOT the reference; only used by tests to show the two differ */
+void lvo_textbook_px(int y, int u, int v, uint8_t bgr[3]);
+
+/* ---- difference + macroblock reduction ---------------------------------------------------- */
+int  lvo_is_nearly_zero(int a, int tol);                      /* image.h:22 */
+/* mask[i] = !IsNearlyZero(cur[i]-ref[i], tol); mb_count[k] = sum of mask over MB k
+ * (k = mby*mb_w + mbx, mb_w = ceil(w/16), mb_h = ceil(h/16)); mb_map[k] = mb_count[k] > mb_thresh.
+ * Any output pointer may be NULL.  Returns changed pixel count. */
+uint32_t lvo_frame_diff_mb(const uint8_t *cur_y, const uint8_t *ref_y, int width, int height,
+                           int tol, int mb_thresh, uint8_t *mask, uint16_t *mb_count, uint8_t *mb_map);
+/* pack a 0/1 byte mask into LSB-first bits, one uint16 per 16-pixel unit (width % 16 == 0) */
+void lvo_pack_mask16(const uint8_t *mask, int width, int height, uint16_t *bits);
+
+/* ---- the fused batch step (what the GPU kernel computes) ---------------------------------- */
+/* i420: n_streams*n_frames frames, stream-major, each Y[w*h] U[w*h/4] V[w*h/4].
+ * prev_luma: n_streams planes; frame 0 of a stream is differenced against it, frame t against
+ * frame t-1 of the batch; on return it holds the last frame's luma (image.c:1553-1561).
+ * bgr: 3*w*h per frame.  mask (bytes, optional), mb_count, mb_map, summary[2] per frame
+ * ({changed_px, changed_mbs}) -- any may be NULL.  n_threads<=1 => single thread. */
+void lvo_convert_diff_batch(const uint8_t *i420, uint8_t *prev_luma, int n_streams, int n_frames,
+                            int width, int height, int tol, int mb_thresh,
+                            uint8_t *bgr, uint8_t *mask, uint16_t *mb_count, uint8_t *mb_map,
+                            uint32_t *summary, int n_threads);
+
+/* ---- background subtraction, the literal WriteBks (MainDlg.cpp:771-835) ------------------- */
+/* out planes: Y -> 16 where |d|<=tol else cur; U,V -> 128 where |d|<=tol else cur. */
+void lvo_write_bks(const uint8_t *cur_i420, const uint8_t *bkd_i420, int width, int height,
+                   int tol, uint8_t *out_i420);
+
+/* ---- object box from the mask (image.c:4818-4848) ----------------------------------------- */
+/* box[4] = {min_x, max_x, min_y, max_y} over mask==1 inside the window [x0..x1]x[y0..y1] (inclusive);
+ * empty => {x1+1, x0-1, y1+1, y0-1} exactly as the reference initialises them. */
+void lvo_object_box(const uint8_t *mask, int width, int x0, int x1, int y0, int y1, int box[4]);
+
+/* ---- synthetic generators; counter based, identical in C / numpy / CUDA --- */
+uint32_t lvo_lowbias32(uint32_t x);
+void lvo_gen_uniform(uint32_t seed, uint32_t stream, uint32_t frame, int width, int height, uint8_t *i420);
+void lvo_gen_camera(uint32_t seed, uint32_t stream, uint32_t frame, int width, int height, uint8_t *i420);
+
+uint32_t lvo_crc32(const uint8_t *p, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
