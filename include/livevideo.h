@@ -1,0 +1,146 @@
+/*
+ * livevideo.h -- C ABI of livevideo-b200: the B200-native replacement for the per-frame hot path
+ * of wonsang/LiveVideo (HMCPT).  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * What each entry replaces in the reference (paths relative to the reference tree):
+ *
+ *   YV12_to_RGB24          ColorSpaceConversions::YV12_to_RGB24, Convert.h:26 (code: cscc.lib,
+ *                          Convert.obj .text+0x350); called at MainDlg.cpp:946,953,960,967,974 and
+ *                          BkdextDlg.cpp:106.  Output contract (bottom-up B,G,R DIB, stride 3*w):
+ *                          MainDlg.cpp:876-882, 985-995.
+ *   FrameDiff_MB           the background / frame difference primitive IsNearlyZero (lib/JM/image.h:22,
+ *                          MainDlg.h:9) as applied per pixel in lib/JM/image.c:4791-4804 and
+ *                          MainDlg.cpp:804-810, plus the 16x16 macroblock grid and "block is ON" scan of
+ *                          lib/JM/image.c:4677-4679, 4981, 5143-5150.
+ *   lv_* (context API)     the same two steps fused in one pass over a batch of frames of many
+ *                          streams, with the previous-frame retention of lib/JM/image.c:1553-1561
+ *                          (prev_frm <- curr_frm) kept as per-stream device state, fed by the planar
+ *                          I420 layout JM emits in lib/JM/output.c:427-451.
+ *
+ * Every entry needs a CUDA device (sm_100a build).  There is no CPU fallback: when no device is
+ * usable the int-returning entries return LV_E_NODEVICE / LV_E_CUDA and the two void legacy entries
+ * print the CUDA error to stderr and abort().
+ */
+#ifndef LIVEVIDEO_H
+#define LIVEVIDEO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(_WIN32)
+#define LV_API __declspec(dllexport)
+#else
+#define LV_API __attribute__((visibility("default")))
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------------------------------ */
+#define LV_OK           0
+#define LV_E_ARG       -1   /* NULL / out-of-range argument                                     */
+#define LV_E_SIZE      -2   /* unsupported geometry (width % 4 != 0 or height % 2 != 0, ...)    */
+#define LV_E_NODEVICE  -3   /* no CUDA device / wrong device index                              */
+#define LV_E_CUDA      -4   /* a CUDA runtime call failed; see lv_last_error()                  */
+#define LV_E_NOMEM     -5   /* host or device allocation failed                                 */
+#define LV_E_STATE     -6   /* call sequence error (e.g. pipeline used before it was created)   */
+
+LV_API const char *lv_strerror(int code);
+LV_API const char *lv_last_error(void);      /* thread-local text of the last CUDA failure */
+LV_API int lv_version(void);                 /* 10000*major + 100*minor + patch */
+LV_API int lv_device_count(void);
+
+/* ---- legacy drop-in entries: host pointers, synchronous, caller owns every buffer ----------------
+ * Same parameter list and meaning as Convert.h:26.  src0 = Y (width*height), src1 = U (Cb), src2 = V
+ * (Cr) (width*height/4 each, tight stride), dst_ori = 3*width*height bytes, bottom-up rows, B,G,R.
+ * Like the original it requires width % 4 == 0 and height % 2 == 0 (the original overruns otherwise);
+ * this build checks and aborts instead of overrunning.  Thread-safe; a per-thread context on the
+ * current CUDA device is created on first use. */
+LV_API void YV12_to_RGB24(unsigned char *src0, unsigned char *src1, unsigned char *src2,
+                          unsigned char *dst_ori, int width, int height);
+
+/* mask[i] = (|cur_y[i] - ref_y[i]| > tol) as 0/1 bytes (the reference's bkd_obj, image.c:4798/4803);
+ * mb_count[k] = number of set mask pixels in macroblock k = mby*mb_w + mbx, mb_w = ceil(width/16),
+ * mb_h = ceil(height/16); mb_map[k] = mb_count[k] > mb_thresh (mb_thresh = 0 is the reference's
+ * "any pixel" rule, image.c:5143-5150).  Any output pointer may be NULL. */
+LV_API void FrameDiff_MB(const unsigned char *cur_y, const unsigned char *ref_y, int width, int height,
+                         int tol, int mb_thresh, unsigned char *mask, unsigned short *mb_count,
+                         unsigned char *mb_map);
+
+/* ---- context API: device pointers, asynchronous on a caller-supplied CUDA stream ------------------ */
+typedef struct lv_ctx lv_ctx;
+
+/* One context per (host thread, device).  max_streams = number of independent camera streams whose
+ * previous-luma state the context keeps (>= 1).  The state starts as all zero, like the calloc'ed
+ * prev_frm of lib/JM/image.c:564-570.  tol in [0,255] (reference default BKD_STR_TOL = 20,
+ * lib/JM/global.h:125), mb_thresh in [0,256]. */
+LV_API int lv_create(int device, int width, int height, int max_streams, int tol, int mb_thresh,
+                     lv_ctx **out);
+LV_API void lv_destroy(lv_ctx *ctx);
+LV_API int lv_set_params(lv_ctx *ctx, int tol, int mb_thresh);
+
+/* Geometry helpers (bytes / element counts per frame). */
+LV_API size_t lv_frame_bytes_i420(const lv_ctx *ctx);   /* 1.5*w*h            */
+LV_API size_t lv_frame_bytes_bgr(const lv_ctx *ctx);    /* 3*w*h              */
+LV_API size_t lv_frame_mask_units(const lv_ctx *ctx);   /* (w/16)*h uint16    */
+LV_API size_t lv_frame_mbs(const lv_ctx *ctx);          /* mb_w*mb_h          */
+
+/* Previous-luma state of one stream (checkpoint / stream migration / static background as reference,
+ * MainDlg.cpp:238-246).  `y` is a host pointer when is_device == 0, else a device pointer. */
+LV_API int lv_set_prev_luma(lv_ctx *ctx, int stream, const uint8_t *y, int is_device, void *cuda_stream);
+LV_API int lv_get_prev_luma(lv_ctx *ctx, int stream, uint8_t *y, int is_device, void *cuda_stream);
+LV_API int lv_reset_prev_luma(lv_ctx *ctx, void *cuda_stream);   /* back to all zero */
+
+/* The fused step.  d_i420 holds n_streams*n_frames frames, stream-major: frame (s,t) starts at byte
+ * (s*n_frames+t)*1.5*w*h and is Y[w*h] U[w*h/4] V[w*h/4] (lib/JM/output.c:427-451).  Stream s maps to
+ * state slot first_stream+s.  Frame t=0 is differenced against the stream's carried previous luma,
+ * frame t>0 against frame t-1 of the batch; afterwards the state holds frame n_frames-1's luma.
+ * Outputs (device pointers; each may be NULL to skip it):
+ *   d_bgr        3*w*h bytes per frame, bottom-up B,G,R (identical to YV12_to_RGB24)
+ *   d_mask_bits  (w/16)*h uint16 per frame; bit i of unit u of row y = mask of pixel (16u+i, y)
+ *   d_mask_bytes w*h bytes per frame, 0/1
+ *   d_mb_count   mb_w*mb_h uint16 per frame;  d_mb_map  mb_w*mb_h bytes per frame
+ *   d_summary    2 uint32 per frame: {changed pixels, changed macroblocks}
+ * Requires width % 16 == 0 and height % 2 == 0. */
+LV_API int lv_convert_diff_batch(lv_ctx *ctx, const uint8_t *d_i420, int first_stream, int n_streams,
+                                 int n_frames, uint8_t *d_bgr, uint16_t *d_mask_bits,
+                                 uint8_t *d_mask_bytes, uint16_t *d_mb_count, uint8_t *d_mb_map,
+                                 uint32_t *d_summary, void *cuda_stream);
+
+/* Conversion only (K2) and difference only (K3) over n frames; same layouts as above.
+ * lv_diff_batch: frame i of d_cur_y (w*h bytes each) against frame i of d_ref_y. */
+LV_API int lv_convert_batch(lv_ctx *ctx, const uint8_t *d_i420, int n_frames, uint8_t *d_bgr,
+                            void *cuda_stream);
+LV_API int lv_diff_batch(lv_ctx *ctx, const uint8_t *d_cur_y, const uint8_t *d_ref_y, int n_frames,
+                         uint16_t *d_mask_bits, uint8_t *d_mask_bytes, uint16_t *d_mb_count,
+                         uint8_t *d_mb_map, uint32_t *d_summary, void *cuda_stream);
+
+/* ---- host-buffer step: pinned, double-buffered H2D -> fused kernel -> D2H ------------------------
+ * The call a host application makes when frames live in host memory (the JM producer hook of
+ * lib/JM/output.c:427-451 writes into the pinned input).  lv_host_alloc / lv_host_free hand out
+ * pinned memory; lv_step_host splits the batch into chunks of `chunk_frames` frames per stream group
+ * and overlaps the upload of chunk k+1 (copy stream) with the kernel of chunk k and the download of
+ * chunk k-1.  Host pointers may also be ordinary pageable memory (slower: staged by the driver).
+ * Outputs may be NULL.  Synchronous: returns when every output is in host memory. */
+LV_API int lv_host_alloc(void **p, size_t bytes);
+LV_API int lv_host_free(void *p);
+LV_API int lv_step_host(lv_ctx *ctx, const uint8_t *h_i420, int first_stream, int n_streams, int n_frames,
+                        uint8_t *h_bgr, uint16_t *h_mask_bits, uint16_t *h_mb_count, uint8_t *h_mb_map,
+                        uint32_t *h_summary);
+
+/* ---- synthetic input (benchmark / tests): stands in for the JM decoder's output --------------------
+ * kind 0 = `uniform`, 1 = `camera`; writes n_streams*n_frames I420 frames, stream-major,
+ * for streams first_stream.. and frames first_frame.. into device memory.  Byte-identical to the same
+ * generator stated in C in oracle/lv_oracle.c. */
+LV_API int lv_gen_synthetic(int kind, uint32_t seed, uint32_t first_stream, uint32_t first_frame, int n_streams,
+                            int n_frames, int width, int height, uint8_t *d_i420, void *cuda_stream);
+
+/* ---- introspection for the benchmark ------------------------------------------------------------- */
+LV_API uint64_t lv_kernel_launches(const lv_ctx *ctx);   /* kernels of this library launched so far */
+LV_API int lv_device_sm_count(const lv_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIVEVIDEO_H */

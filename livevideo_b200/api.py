@@ -1,0 +1,263 @@
+"""Host-side mirror of the reference's interface for the hot path, over the C ABI.
+
+* ``ColorSpaceConversions`` -- same class/method name and argument meaning as the reference's
+  ``class ColorSpaceConversions`` (Convert.h:19-31): ``YV12_to_RGB24(src0, src1, src2, dst_ori, width, height)``
+  fills ``dst_ori`` in place (bottom-up B,G,R).  The five converters the application never calls are
+  declared and raise NotImplementedError.
+* ``FrameDiff_MB`` -- the difference primitive extracted from lib/JM/image.c:4791-4804 / 5143-5150.
+* ``Context`` -- the batched device API (lv_create ... lv_destroy): fused conversion + difference over
+  many streams with the per-stream previous-luma state of lib/JM/image.c:1553-1561.
+
+PyTorch is used only as the owner of device memory and streams; every computation happens in
+liblivevideo.so (hand-written sm_100a kernels).  There is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+DEFAULT_TOL = 20        # BKD_STR_TOL, lib/JM/global.h:125
+DEFAULT_MB_THRESH = 0   # "any changed pixel", lib/JM/image.c:5143-5150
+
+
+def _host_ptr(a, dtype, nbytes, name, writable=False):
+    if not isinstance(a, np.ndarray):
+        raise TypeError(f"{name}: expected a numpy array")
+    if a.dtype != dtype or not a.flags.c_contiguous:
+        raise ValueError(f"{name}: expected a C-contiguous {np.dtype(dtype).name} array")
+    if a.nbytes < nbytes:
+        raise ValueError(f"{name}: needs {nbytes} bytes, has {a.nbytes}")
+    if writable and not a.flags.writeable:
+        raise ValueError(f"{name}: not writable")
+    return a.ctypes.data
+
+
+class ColorSpaceConversions:
+    """Drop-in mirror of the reference class (Convert.h:19-31)."""
+
+    def __init__(self):
+        capi.lib()   # fail now if the CUDA library is missing
+
+    def YV12_to_RGB24(self, src0, src1, src2, dst_ori, width, height):
+        px = width * height
+        if width <= 0 or height <= 0:
+            return
+        if width % 4 or height % 2:
+            raise ValueError("YV12_to_RGB24 needs width % 4 == 0 and height % 2 == 0 (the original overruns)")
+        capi.lib().YV12_to_RGB24(_host_ptr(src0, np.uint8, px, "src0"), _host_ptr(src1, np.uint8, px // 4, "src1"),
+                                 _host_ptr(src2, np.uint8, px // 4, "src2"),
+                                 _host_ptr(dst_ori, np.uint8, 3 * px, "dst_ori", True), width, height)
+
+    def _unused(self, *a, **k):
+        raise NotImplementedError("never called by the application (grep pCon. -> only YV12_to_RGB24); out of scope")
+
+    RGB24_to_YV12 = YVU9_to_YV12 = YUY2_to_YV12 = YV12_to_YVU9 = YV12_to_YUY2 = _unused
+
+
+def FrameDiff_MB(cur_y, ref_y, width, height, tol=DEFAULT_TOL, mb_thresh=DEFAULT_MB_THRESH, mask=None,
+                 mb_count=None, mb_map=None):
+    """Host-pointer difference entry.  Output arrays are allocated when not given; returns (mask, mb_count, mb_map)."""
+    px = width * height
+    mbs = ((width + 15) // 16) * ((height + 15) // 16)
+    if mask is None:
+        mask = np.empty(px, dtype=np.uint8)
+    if mb_count is None:
+        mb_count = np.empty(mbs, dtype=np.uint16)
+    if mb_map is None:
+        mb_map = np.empty(mbs, dtype=np.uint8)
+    if width <= 0 or height <= 0:
+        return mask, mb_count, mb_map
+    capi.lib().FrameDiff_MB(_host_ptr(cur_y, np.uint8, px, "cur_y"), _host_ptr(ref_y, np.uint8, px, "ref_y"), width,
+                            height, int(tol), int(mb_thresh), _host_ptr(mask, np.uint8, px, "mask", True),
+                            _host_ptr(mb_count, np.uint16, 2 * mbs, "mb_count", True),
+                            _host_ptr(mb_map, np.uint8, mbs, "mb_map", True))
+    return mask, mb_count, mb_map
+
+
+def _dev_ptr(t, dtype, numel, name, device):
+    import torch
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA tensor")
+    if t.device.index != device:
+        raise ValueError(f"{name}: tensor is on cuda:{t.device.index}, context is on cuda:{device}")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous {dtype} tensor")
+    if t.numel() < numel:
+        raise ValueError(f"{name}: needs {numel} elements, has {t.numel()}")
+    return t.data_ptr()
+
+
+def _stream_handle(stream):
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+class Context:
+    """lv_ctx: fused conversion + frame difference for `max_streams` camera streams of one geometry."""
+
+    def __init__(self, width, height, max_streams=1, tol=DEFAULT_TOL, mb_thresh=DEFAULT_MB_THRESH, device=0):
+        self._h = C.c_void_p()
+        L = capi.lib()
+        capi.check(L.lv_create(device, width, height, max_streams, tol, mb_thresh, C.byref(self._h)), "lv_create")
+        self.device, self.width, self.height, self.max_streams = device, width, height, max_streams
+        self.px = width * height
+        self.frame_bytes = L.lv_frame_bytes_i420(self._h)
+        self.bgr_bytes = L.lv_frame_bytes_bgr(self._h)
+        self.mask_units = L.lv_frame_mask_units(self._h)
+        self.mbs = L.lv_frame_mbs(self._h)
+        self.mb_w, self.mb_h = (width + 15) // 16, (height + 15) // 16
+
+    def close(self):
+        if self._h:
+            capi.lib().lv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_params(self, tol, mb_thresh):
+        capi.check(capi.lib().lv_set_params(self._h, tol, mb_thresh), "lv_set_params")
+
+    @property
+    def kernel_launches(self):
+        return int(capi.lib().lv_kernel_launches(self._h))
+
+    @property
+    def sm_count(self):
+        return int(capi.lib().lv_device_sm_count(self._h))
+
+    # ---- previous-luma state ---------------------------------------------------------------------
+    def set_prev_luma(self, stream, y, cuda_stream=None):
+        if isinstance(y, np.ndarray):
+            capi.check(capi.lib().lv_set_prev_luma(self._h, stream, _host_ptr(y, np.uint8, self.px, "y"), 0,
+                                                   _stream_handle(cuda_stream)), "lv_set_prev_luma")
+        else:
+            import torch
+            capi.check(capi.lib().lv_set_prev_luma(self._h, stream, _dev_ptr(y, torch.uint8, self.px, "y", self.device),
+                                                   1, _stream_handle(cuda_stream)), "lv_set_prev_luma")
+
+    def get_prev_luma(self, stream, cuda_stream=None):
+        out = np.empty(self.px, dtype=np.uint8)
+        capi.check(capi.lib().lv_get_prev_luma(self._h, stream, out.ctypes.data, 0, _stream_handle(cuda_stream)),
+                   "lv_get_prev_luma")
+        return out
+
+    def reset_prev_luma(self, cuda_stream=None):
+        capi.check(capi.lib().lv_reset_prev_luma(self._h, _stream_handle(cuda_stream)), "lv_reset_prev_luma")
+
+    # ---- device API --------------------------------------------------------------------------------
+    def alloc_outputs(self, n, bgr=True, mask_bits=False, mask_bytes=False):
+        """Device output tensors for n frames."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        out = {
+            "bgr": torch.empty(n * self.bgr_bytes, dtype=torch.uint8, device=dev) if bgr else None,
+            "mask_bits": torch.empty(n * self.mask_units, dtype=torch.int16, device=dev) if mask_bits else None,
+            "mask_bytes": torch.empty(n * self.px, dtype=torch.uint8, device=dev) if mask_bytes else None,
+            "mb_count": torch.empty(n * self.mbs, dtype=torch.int16, device=dev),
+            "mb_map": torch.empty(n * self.mbs, dtype=torch.uint8, device=dev),
+            "summary": torch.empty(n * 2, dtype=torch.int32, device=dev),
+        }
+        return out
+
+    def convert_diff_batch(self, i420, n_streams, n_frames, out, first_stream=0, cuda_stream=None):
+        """One fused launch over n_streams*n_frames frames resident in device memory (asynchronous)."""
+        import torch
+        n = n_streams * n_frames
+        d = self.device
+        capi.check(capi.lib().lv_convert_diff_batch(
+            self._h, _dev_ptr(i420, torch.uint8, n * self.frame_bytes, "i420", d), first_stream, n_streams, n_frames,
+            _dev_ptr(out.get("bgr"), torch.uint8, n * self.bgr_bytes, "bgr", d),
+            _dev_ptr(out.get("mask_bits"), torch.int16, n * self.mask_units, "mask_bits", d),
+            _dev_ptr(out.get("mask_bytes"), torch.uint8, n * self.px, "mask_bytes", d),
+            _dev_ptr(out.get("mb_count"), torch.int16, n * self.mbs, "mb_count", d),
+            _dev_ptr(out.get("mb_map"), torch.uint8, n * self.mbs, "mb_map", d),
+            _dev_ptr(out.get("summary"), torch.int32, n * 2, "summary", d),
+            _stream_handle(cuda_stream)), "lv_convert_diff_batch")
+
+    def convert_batch(self, i420, n_frames, bgr, cuda_stream=None):
+        import torch
+        d = self.device
+        capi.check(capi.lib().lv_convert_batch(
+            self._h, _dev_ptr(i420, torch.uint8, n_frames * self.frame_bytes, "i420", d), n_frames,
+            _dev_ptr(bgr, torch.uint8, n_frames * self.bgr_bytes, "bgr", d), _stream_handle(cuda_stream)),
+            "lv_convert_batch")
+
+    def diff_batch(self, cur_y, ref_y, n_frames, out, cuda_stream=None):
+        import torch
+        d = self.device
+        capi.check(capi.lib().lv_diff_batch(
+            self._h, _dev_ptr(cur_y, torch.uint8, n_frames * self.px, "cur_y", d),
+            _dev_ptr(ref_y, torch.uint8, n_frames * self.px, "ref_y", d), n_frames,
+            _dev_ptr(out.get("mask_bits"), torch.int16, n_frames * self.mask_units, "mask_bits", d),
+            _dev_ptr(out.get("mask_bytes"), torch.uint8, n_frames * self.px, "mask_bytes", d),
+            _dev_ptr(out.get("mb_count"), torch.int16, n_frames * self.mbs, "mb_count", d),
+            _dev_ptr(out.get("mb_map"), torch.uint8, n_frames * self.mbs, "mb_map", d),
+            _dev_ptr(out.get("summary"), torch.int32, n_frames * 2, "summary", d), _stream_handle(cuda_stream)),
+            "lv_diff_batch")
+
+    # ---- host API ------------------------------------------------------------------------------------
+    def step_host(self, i420, n_streams, n_frames, bgr=None, mask_bits=None, mb_count=None, mb_map=None,
+                  summary=None, first_stream=0):
+        """Host buffers in, host buffers out (numpy arrays, ideally from `pinned()`); synchronous."""
+        n = n_streams * n_frames
+
+        def p(a, dt, nb, name, w=True):
+            return None if a is None else _host_ptr(a, dt, nb, name, w)
+        capi.check(capi.lib().lv_step_host(
+            self._h, _host_ptr(i420, np.uint8, n * self.frame_bytes, "i420"), first_stream, n_streams, n_frames,
+            p(bgr, np.uint8, n * self.bgr_bytes, "bgr"), p(mask_bits, np.uint16, 2 * n * self.mask_units, "mask_bits"),
+            p(mb_count, np.uint16, 2 * n * self.mbs, "mb_count"), p(mb_map, np.uint8, n * self.mbs, "mb_map"),
+            p(summary, np.uint32, 8 * n, "summary")), "lv_step_host")
+
+
+class PinnedArray:
+    """numpy view of pinned host memory from lv_host_alloc (freed with the object)."""
+
+    def __init__(self, nbytes, dtype=np.uint8):
+        self._p = C.c_void_p()
+        capi.check(capi.lib().lv_host_alloc(C.byref(self._p), nbytes), "lv_host_alloc")
+        buf = (C.c_uint8 * nbytes).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dtype)
+
+    def __del__(self):
+        try:
+            if self._p:
+                capi.lib().lv_host_free(self._p)
+                self._p = C.c_void_p()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def pinned(nbytes, dtype=np.uint8):
+    return PinnedArray(nbytes, dtype)
+
+
+def gen_synthetic(kind, seed, first_stream, first_frame, n_streams, n_frames, width, height, out=None, device=0,
+                  cuda_stream=None):
+    """Synthetic I420 frames on the device (`uniform` or `camera` generator)."""
+    import torch
+    n = n_streams * n_frames
+    fb = width * height * 3 // 2
+    if out is None:
+        out = torch.empty(n * fb, dtype=torch.uint8, device=torch.device("cuda", device))
+    with torch.cuda.device(device):
+        capi.check(capi.lib().lv_gen_synthetic({"uniform": 0, "camera": 1}[kind], seed, first_stream, first_frame,
+                                               n_streams, n_frames, width, height,
+                                               _dev_ptr(out, torch.uint8, n * fb, "out", device),
+                                               _stream_handle(cuda_stream)), "lv_gen_synthetic")
+    return out

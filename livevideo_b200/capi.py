@@ -1,0 +1,77 @@
+"""ctypes binding of include/livevideo.h (the C ABI).  Loads the in-tree liblivevideo.so and nothing else:
+there is no CPU fallback -- a missing library or a missing CUDA device raises."""
+import ctypes as C
+import os
+
+from . import _build
+
+_u8p = C.POINTER(C.c_uint8)
+_u16p = C.POINTER(C.c_uint16)
+_u32p = C.POINTER(C.c_uint32)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); one row per symbol declared in include/livevideo.h
+SYMBOLS = {
+    "lv_strerror": (C.c_char_p, [C.c_int]),
+    "lv_last_error": (C.c_char_p, []),
+    "lv_version": (C.c_int, []),
+    "lv_device_count": (C.c_int, []),
+    "YV12_to_RGB24": (None, [_vp, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "FrameDiff_MB": (None, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "lv_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "lv_destroy": (None, [_vp]),
+    "lv_set_params": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "lv_frame_bytes_i420": (C.c_size_t, [_vp]),
+    "lv_frame_bytes_bgr": (C.c_size_t, [_vp]),
+    "lv_frame_mask_units": (C.c_size_t, [_vp]),
+    "lv_frame_mbs": (C.c_size_t, [_vp]),
+    "lv_set_prev_luma": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
+    "lv_get_prev_luma": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
+    "lv_reset_prev_luma": (C.c_int, [_vp, _vp]),
+    "lv_convert_diff_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lv_convert_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "lv_diff_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lv_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
+    "lv_host_free": (C.c_int, [_vp]),
+    "lv_step_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lv_kernel_launches": (C.c_uint64, [_vp]),
+    "lv_device_sm_count": (C.c_int, [_vp]),
+    "lv_gen_synthetic": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   _vp, _vp]),
+}
+
+_lib = None
+
+
+class LiveVideoError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        msg = lib().lv_strerror(code).decode()
+        detail = lib().lv_last_error().decode()
+        super().__init__(f"{where}: {msg} ({code})" + (f": {detail}" if detail else ""))
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if liblivevideo.so has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -m livevideo_b200._build` (needs nvcc). "
+                               "livevideo_b200 has no CPU fallback.")
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)          # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code, where):
+    if code != 0:
+        raise LiveVideoError(code, where)

@@ -1,0 +1,508 @@
+// lv_capi.cu -- the C ABI of include/livevideo.h over the CUDA runtime.
+//
+// Host-side logic only: argument checking, the per-stream previous-luma state (ping-pong planes, so
+// a launch never reads a plane that the same launch rewrites), the pinned double-buffered host step
+// and the two legacy drop-in entries.  No CPU implementation of the pixel math exists here or
+// anywhere in the product: if CUDA is unusable every entry fails loudly.
+#include "../../include/livevideo.h"
+#include "lv_kernels.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+namespace {
+
+thread_local char g_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    snprintf(g_err, sizeof g_err, "%s: %s (%d)", what, cudaGetErrorString(e), (int)e);
+    return e == cudaErrorMemoryAllocation ? LV_E_NOMEM : LV_E_CUDA;
+}
+
+#define LV_CUDA(call)                                                  \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);            \
+    } while (0)
+
+int launch_result(int r, uint64_t &counter)
+{
+    if (r < 0) return cuda_fail((cudaError_t)(-r), "kernel launch");
+    counter += (uint64_t)r;
+    return LV_OK;
+}
+
+}  // namespace
+
+struct lv_ctx {
+    int device = 0;
+    int sm_count = 0;
+    lv::Geom g{};
+    int max_streams = 0;
+    int tol = 20, mb_thresh = 0;
+    uint8_t *state[2] = {nullptr, nullptr};   // ping-pong previous-luma planes, max_streams x px each
+    int cur = 0;                              // state[cur] holds the live previous luma
+    uint64_t launches = 0;
+    // host-step pipeline (created on first lv_step_host)
+    cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
+    static const int kSlots = 3;
+    uint8_t *d_in[kSlots] = {}, *d_bgr[kSlots] = {};
+    uint16_t *d_bits[kSlots] = {}, *d_cnt[kSlots] = {};
+    uint8_t *d_map[kSlots] = {};
+    uint32_t *d_sum[kSlots] = {};
+    cudaEvent_t ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
+    int slot_frames = 0;                      // capacity of one slot in frames
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+bool geom_fast(int w, int h) { return w >= 16 && h >= 2 && w % 16 == 0 && h % 2 == 0; }
+
+void free_pipeline(lv_ctx *c)
+{
+    for (int i = 0; i < lv_ctx::kSlots; i++) {
+        cudaFree(c->d_in[i]); cudaFree(c->d_bgr[i]); cudaFree(c->d_bits[i]); cudaFree(c->d_cnt[i]);
+        cudaFree(c->d_map[i]); cudaFree(c->d_sum[i]);
+        c->d_in[i] = c->d_bgr[i] = c->d_map[i] = nullptr; c->d_bits[i] = c->d_cnt[i] = nullptr; c->d_sum[i] = nullptr;
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+        c->ev_in[i] = c->ev_k[i] = c->ev_out[i] = nullptr;
+    }
+    if (c->s_copy_in) cudaStreamDestroy(c->s_copy_in);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_copy_out) cudaStreamDestroy(c->s_copy_out);
+    c->s_copy_in = c->s_compute = c->s_copy_out = nullptr;
+    c->slot_frames = 0;
+}
+
+// Device slots for the host step: `frames` frames each.
+int ensure_pipeline(lv_ctx *c, int frames)
+{
+    if (c->slot_frames >= frames) return LV_OK;
+    free_pipeline(c);
+    const lv::Geom &g = c->g;
+    LV_CUDA(cudaStreamCreateWithFlags(&c->s_copy_in, cudaStreamNonBlocking));
+    LV_CUDA(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+    LV_CUDA(cudaStreamCreateWithFlags(&c->s_copy_out, cudaStreamNonBlocking));
+    const size_t mbs = (size_t)g.mb_w * g.mb_h;
+    for (int i = 0; i < lv_ctx::kSlots; i++) {
+        LV_CUDA(cudaMalloc(&c->d_in[i], g.frame * frames));
+        LV_CUDA(cudaMalloc(&c->d_bgr[i], 3 * g.px * frames));
+        LV_CUDA(cudaMalloc(&c->d_bits[i], sizeof(uint16_t) * (size_t)g.units * g.h * frames));
+        LV_CUDA(cudaMalloc(&c->d_cnt[i], sizeof(uint16_t) * mbs * frames));
+        LV_CUDA(cudaMalloc(&c->d_map[i], mbs * frames));
+        LV_CUDA(cudaMalloc(&c->d_sum[i], sizeof(uint32_t) * 2 * frames));
+        LV_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        LV_CUDA(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+        LV_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    }
+    c->slot_frames = frames;
+    return LV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *lv_strerror(int code)
+{
+    switch (code) {
+    case LV_OK: return "ok";
+    case LV_E_ARG: return "invalid argument";
+    case LV_E_SIZE: return "unsupported frame geometry";
+    case LV_E_NODEVICE: return "no usable CUDA device";
+    case LV_E_CUDA: return "CUDA runtime error";
+    case LV_E_NOMEM: return "out of memory";
+    case LV_E_STATE: return "invalid call sequence";
+    default: return "unknown error";
+    }
+}
+
+const char *lv_last_error(void) { return g_err; }
+int lv_version(void) { return 100; }
+
+int lv_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int lv_create(int device, int width, int height, int max_streams, int tol, int mb_thresh, lv_ctx **out)
+{
+    if (!out) return LV_E_ARG;
+    *out = nullptr;
+    if (max_streams < 1 || tol < 0 || tol > 255 || mb_thresh < 0 || mb_thresh > 256) return LV_E_ARG;
+    if (width < 4 || height < 2 || width % 4 != 0 || height % 2 != 0) return LV_E_SIZE;
+    if ((size_t)width * height > ((size_t)1 << 30)) return LV_E_SIZE;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cuda_fail(e, "cudaGetDeviceCount");
+        return LV_E_NODEVICE;
+    }
+    if (device < 0 || device >= n) return LV_E_NODEVICE;
+    DeviceGuard guard(device);
+    if (!guard.ok) return LV_E_NODEVICE;
+    lv_ctx *c = new (std::nothrow) lv_ctx;
+    if (!c) return LV_E_NOMEM;
+    c->device = device;
+    c->g = lv::make_geom(width, height);
+    c->max_streams = max_streams;
+    c->tol = tol;
+    c->mb_thresh = mb_thresh;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    const size_t bytes = c->g.px * (size_t)max_streams;
+    for (int i = 0; i < 2; i++) {
+        e = cudaMalloc(&c->state[i], bytes);
+        if (e == cudaSuccess) e = cudaMemset(c->state[i], 0, bytes);   // calloc'ed prev_frm, image.c:564-570
+        if (e != cudaSuccess) {
+            int rc = cuda_fail(e, "state allocation");
+            lv_destroy(c);
+            return rc;
+        }
+    }
+    *out = c;
+    return LV_OK;
+}
+
+void lv_destroy(lv_ctx *c)
+{
+    if (!c) return;
+    DeviceGuard guard(c->device);
+    free_pipeline(c);
+    cudaFree(c->state[0]);
+    cudaFree(c->state[1]);
+    delete c;
+}
+
+int lv_set_params(lv_ctx *c, int tol, int mb_thresh)
+{
+    if (!c || tol < 0 || tol > 255 || mb_thresh < 0 || mb_thresh > 256) return LV_E_ARG;
+    c->tol = tol;
+    c->mb_thresh = mb_thresh;
+    return LV_OK;
+}
+
+size_t lv_frame_bytes_i420(const lv_ctx *c) { return c ? c->g.frame : 0; }
+size_t lv_frame_bytes_bgr(const lv_ctx *c) { return c ? 3 * c->g.px : 0; }
+size_t lv_frame_mask_units(const lv_ctx *c) { return c ? (size_t)c->g.units * c->g.h : 0; }
+size_t lv_frame_mbs(const lv_ctx *c) { return c ? (size_t)c->g.mb_w * c->g.mb_h : 0; }
+uint64_t lv_kernel_launches(const lv_ctx *c) { return c ? c->launches : 0; }
+int lv_device_sm_count(const lv_ctx *c) { return c ? c->sm_count : 0; }
+
+int lv_set_prev_luma(lv_ctx *c, int stream, const uint8_t *y, int is_device, void *cuda_stream)
+{
+    if (!c || !y || stream < 0 || stream >= c->max_streams) return LV_E_ARG;
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    LV_CUDA(cudaMemcpyAsync(c->state[c->cur] + (size_t)stream * c->g.px, y, c->g.px,
+                            is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (!is_device) LV_CUDA(cudaStreamSynchronize(st));
+    return LV_OK;
+}
+
+int lv_get_prev_luma(lv_ctx *c, int stream, uint8_t *y, int is_device, void *cuda_stream)
+{
+    if (!c || !y || stream < 0 || stream >= c->max_streams) return LV_E_ARG;
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    LV_CUDA(cudaMemcpyAsync(y, c->state[c->cur] + (size_t)stream * c->g.px, c->g.px,
+                            is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!is_device) LV_CUDA(cudaStreamSynchronize(st));
+    return LV_OK;
+}
+
+int lv_reset_prev_luma(lv_ctx *c, void *cuda_stream)
+{
+    if (!c) return LV_E_ARG;
+    DeviceGuard guard(c->device);
+    LV_CUDA(cudaMemsetAsync(c->state[c->cur], 0, c->g.px * (size_t)c->max_streams, (cudaStream_t)cuda_stream));
+    return LV_OK;
+}
+
+int lv_convert_diff_batch(lv_ctx *c, const uint8_t *d_i420, int first_stream, int n_streams, int n_frames,
+                          uint8_t *d_bgr, uint16_t *d_mask_bits, uint8_t *d_mask_bytes, uint16_t *d_mb_count,
+                          uint8_t *d_mb_map, uint32_t *d_summary, void *cuda_stream)
+{
+    if (!c || !d_i420) return LV_E_ARG;
+    if (n_streams < 0 || n_frames < 0 || first_stream < 0 || first_stream + n_streams > c->max_streams) return LV_E_ARG;
+    if (!geom_fast(c->g.w, c->g.h)) return LV_E_SIZE;
+    if (n_streams == 0 || n_frames == 0) return LV_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (d_summary) LV_CUDA(cudaMemsetAsync(d_summary, 0, sizeof(uint32_t) * 2 * (size_t)n_streams * n_frames, st));
+    lv::StepArgs a{};
+    a.g = c->g;
+    a.i420 = d_i420;
+    a.state_in = c->state[c->cur] + (size_t)first_stream * c->g.px;
+    a.state_out = c->state[c->cur ^ 1] + (size_t)first_stream * c->g.px;
+    a.n_streams = n_streams; a.n_frames = n_frames;
+    a.tol = c->tol; a.mb_thresh = c->mb_thresh;
+    a.bgr = d_bgr; a.mask_bits = d_mask_bits; a.mask_bytes = d_mask_bytes;
+    a.mb_count = d_mb_count; a.mb_map = d_mb_map; a.summary = d_summary;
+    int rc = launch_result(lv::launch_step(a, st), c->launches);
+    if (rc != LV_OK) return rc;
+    // Streams outside [first_stream, first_stream+n_streams) keep their state: carry it over to the
+    // plane set that becomes live.  (Whole-context batches, the common case, copy nothing.)
+    if (first_stream > 0)
+        LV_CUDA(cudaMemcpyAsync(c->state[c->cur ^ 1], c->state[c->cur], (size_t)first_stream * c->g.px,
+                                cudaMemcpyDeviceToDevice, st));
+    if (first_stream + n_streams < c->max_streams) {
+        const size_t off = (size_t)(first_stream + n_streams) * c->g.px;
+        LV_CUDA(cudaMemcpyAsync(c->state[c->cur ^ 1] + off, c->state[c->cur] + off,
+                                (size_t)(c->max_streams - first_stream - n_streams) * c->g.px,
+                                cudaMemcpyDeviceToDevice, st));
+    }
+    c->cur ^= 1;
+    return LV_OK;
+}
+
+int lv_convert_batch(lv_ctx *c, const uint8_t *d_i420, int n_frames, uint8_t *d_bgr, void *cuda_stream)
+{
+    if (!c || !d_i420 || !d_bgr || n_frames < 0) return LV_E_ARG;
+    if (!geom_fast(c->g.w, c->g.h)) return LV_E_SIZE;
+    if (n_frames == 0) return LV_OK;
+    DeviceGuard guard(c->device);
+    return launch_result(lv::launch_convert(c->g, d_i420, n_frames, d_bgr, (cudaStream_t)cuda_stream), c->launches);
+}
+
+int lv_diff_batch(lv_ctx *c, const uint8_t *d_cur_y, const uint8_t *d_ref_y, int n_frames, uint16_t *d_mask_bits,
+                  uint8_t *d_mask_bytes, uint16_t *d_mb_count, uint8_t *d_mb_map, uint32_t *d_summary,
+                  void *cuda_stream)
+{
+    if (!c || !d_cur_y || !d_ref_y || n_frames < 0) return LV_E_ARG;
+    if (!geom_fast(c->g.w, c->g.h)) return LV_E_SIZE;
+    if (n_frames == 0) return LV_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (d_summary) LV_CUDA(cudaMemsetAsync(d_summary, 0, sizeof(uint32_t) * 2 * (size_t)n_frames, st));
+    lv::DiffArgs a{};
+    a.g = c->g; a.cur_y = d_cur_y; a.ref_y = d_ref_y; a.n_frames = n_frames;
+    a.tol = c->tol; a.mb_thresh = c->mb_thresh;
+    a.mask_bits = d_mask_bits; a.mask_bytes = d_mask_bytes; a.mb_count = d_mb_count; a.mb_map = d_mb_map;
+    a.summary = d_summary;
+    return launch_result(lv::launch_diff(a, st), c->launches);
+}
+
+int lv_host_alloc(void **p, size_t bytes)
+{
+    if (!p) return LV_E_ARG;
+    *p = nullptr;
+    LV_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+    return LV_OK;
+}
+
+int lv_host_free(void *p)
+{
+    if (!p) return LV_OK;
+    LV_CUDA(cudaFreeHost(p));
+    return LV_OK;
+}
+
+// Host step.  The batch is cut along the frame axis into chunks (all streams, a few frames each):
+// chunk k's previous luma is chunk k-1's last frame, which is exactly what the carried state holds
+// after chunk k-1's kernel, so chunking does not change any result.
+//   copy-in stream : H2D chunk k          (waits until the kernel that last used the slot is done)
+//   compute stream : kernel chunk k       (waits for its H2D)
+//   copy-out stream: D2H chunk k          (waits for its kernel)
+// With 3 slots the upload of k+1, the kernel of k and the download of k-1 are in flight together.
+int lv_step_host(lv_ctx *c, const uint8_t *h_i420, int first_stream, int n_streams, int n_frames, uint8_t *h_bgr,
+                 uint16_t *h_mask_bits, uint16_t *h_mb_count, uint8_t *h_mb_map, uint32_t *h_summary)
+{
+    if (!c || !h_i420) return LV_E_ARG;
+    if (n_streams < 0 || n_frames < 0 || first_stream < 0 || first_stream + n_streams > c->max_streams) return LV_E_ARG;
+    if (!geom_fast(c->g.w, c->g.h)) return LV_E_SIZE;
+    if (n_streams == 0 || n_frames == 0) return LV_OK;
+    DeviceGuard guard(c->device);
+    const lv::Geom &g = c->g;
+    const size_t mbs = (size_t)g.mb_w * g.mb_h, units = (size_t)g.units * g.h;
+
+    // chunk = cf frames of every stream; aim at ~32 MiB of input per chunk, at least 1 frame
+    int cf = (int)(((size_t)32 << 20) / (g.frame * (size_t)n_streams));
+    if (cf < 1) cf = 1;
+    if (cf > n_frames) cf = n_frames;
+    // a slot must hold one chunk; streams are cut too if even one frame of all streams is too large
+    int cs = n_streams;
+    const size_t cap_frames = ((size_t)256 << 20) / g.frame > 0 ? ((size_t)256 << 20) / g.frame : 1;
+    if ((size_t)cs * cf > cap_frames) { cf = 1; if ((size_t)cs > cap_frames) cs = (int)cap_frames; }
+    int rc = ensure_pipeline(c, cs * cf);
+    if (rc != LV_OK) return rc;
+
+    int k = 0;
+    for (int s0 = 0; s0 < n_streams; s0 += cs) {
+        const int ns = n_streams - s0 < cs ? n_streams - s0 : cs;
+        for (int t0 = 0; t0 < n_frames; t0 += cf, k++) {
+            const int nt = n_frames - t0 < cf ? n_frames - t0 : cf;
+            const int slot = k % lv_ctx::kSlots;
+            // the slot's previous download must have drained before its buffers are reused
+            if (k >= lv_ctx::kSlots) {
+                LV_CUDA(cudaStreamWaitEvent(c->s_copy_in, c->ev_k[slot], 0));
+                LV_CUDA(cudaStreamWaitEvent(c->s_compute, c->ev_out[slot], 0));
+            }
+            // H2D: per stream one strided piece (frames t0..t0+nt of stream s are contiguous in the host batch)
+            for (int s = 0; s < ns; s++) {
+                const uint8_t *src = h_i420 + ((size_t)(s0 + s) * n_frames + t0) * g.frame;
+                LV_CUDA(cudaMemcpyAsync(c->d_in[slot] + (size_t)s * nt * g.frame, src, (size_t)nt * g.frame,
+                                        cudaMemcpyHostToDevice, c->s_copy_in));
+            }
+            LV_CUDA(cudaEventRecord(c->ev_in[slot], c->s_copy_in));
+            LV_CUDA(cudaStreamWaitEvent(c->s_compute, c->ev_in[slot], 0));
+            rc = lv_convert_diff_batch(c, c->d_in[slot], first_stream + s0, ns, nt, h_bgr ? c->d_bgr[slot] : nullptr,
+                                       h_mask_bits ? c->d_bits[slot] : nullptr, nullptr,
+                                       h_mb_count ? c->d_cnt[slot] : nullptr, h_mb_map ? c->d_map[slot] : nullptr,
+                                       h_summary ? c->d_sum[slot] : nullptr, c->s_compute);
+            if (rc != LV_OK) return rc;
+            LV_CUDA(cudaEventRecord(c->ev_k[slot], c->s_compute));
+            LV_CUDA(cudaStreamWaitEvent(c->s_copy_out, c->ev_k[slot], 0));
+            for (int s = 0; s < ns; s++) {
+                const size_t hf = (size_t)(s0 + s) * n_frames + t0, df = (size_t)s * nt;
+                if (h_bgr)
+                    LV_CUDA(cudaMemcpyAsync(h_bgr + hf * 3 * g.px, c->d_bgr[slot] + df * 3 * g.px, (size_t)nt * 3 * g.px,
+                                            cudaMemcpyDeviceToHost, c->s_copy_out));
+                if (h_mask_bits)
+                    LV_CUDA(cudaMemcpyAsync(h_mask_bits + hf * units, c->d_bits[slot] + df * units,
+                                            sizeof(uint16_t) * nt * units, cudaMemcpyDeviceToHost, c->s_copy_out));
+                if (h_mb_count)
+                    LV_CUDA(cudaMemcpyAsync(h_mb_count + hf * mbs, c->d_cnt[slot] + df * mbs, sizeof(uint16_t) * nt * mbs,
+                                            cudaMemcpyDeviceToHost, c->s_copy_out));
+                if (h_mb_map)
+                    LV_CUDA(cudaMemcpyAsync(h_mb_map + hf * mbs, c->d_map[slot] + df * mbs, (size_t)nt * mbs,
+                                            cudaMemcpyDeviceToHost, c->s_copy_out));
+                if (h_summary)
+                    LV_CUDA(cudaMemcpyAsync(h_summary + hf * 2, c->d_sum[slot] + df * 2, sizeof(uint32_t) * 2 * nt,
+                                            cudaMemcpyDeviceToHost, c->s_copy_out));
+            }
+            LV_CUDA(cudaEventRecord(c->ev_out[slot], c->s_copy_out));
+        }
+    }
+    LV_CUDA(cudaStreamSynchronize(c->s_copy_out));
+    LV_CUDA(cudaStreamSynchronize(c->s_compute));
+    return LV_OK;
+}
+
+// ---- legacy drop-in entries ------------------------------------------------------------------------
+
+namespace {
+
+[[noreturn]] void legacy_die(const char *fn, const char *msg)
+{
+    fprintf(stderr, "livevideo-b200: %s: %s (%s)\n", fn, msg, g_err);
+    abort();
+}
+
+struct LegacyBuf {
+    uint8_t *d = nullptr;
+    size_t cap = 0;
+    uint8_t *get(size_t n)
+    {
+        if (n > cap) {
+            cudaFree(d);
+            d = nullptr;
+            cap = 0;
+            if (cudaMalloc(&d, n) != cudaSuccess) return nullptr;
+            cap = n;
+        }
+        return d;
+    }
+};
+thread_local LegacyBuf t_in, t_out;
+thread_local cudaStream_t t_stream = nullptr;
+
+cudaStream_t legacy_stream(const char *fn)
+{
+    if (!t_stream && cudaStreamCreateWithFlags(&t_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cuda_fail(cudaGetLastError(), "cudaStreamCreate");
+        legacy_die(fn, "no usable CUDA device");
+    }
+    return t_stream;
+}
+
+}  // namespace
+
+void YV12_to_RGB24(unsigned char *src0, unsigned char *src1, unsigned char *src2, unsigned char *dst_ori, int width,
+                   int height)
+{
+    static const char *fn = "YV12_to_RGB24";
+    if (!src0 || !src1 || !src2 || !dst_ori) legacy_die(fn, "NULL plane");
+    if (width <= 0 || height <= 0) return;   // the original's loops run zero times
+    if (width % 4 != 0 || height % 2 != 0) legacy_die(fn, "needs width % 4 == 0 and height % 2 == 0 (the original overruns)");
+    cudaStream_t st = legacy_stream(fn);
+    const size_t px = (size_t)width * height;
+    uint8_t *din = t_in.get(px + px / 2), *dout = t_out.get(3 * px);
+    if (!din || !dout) legacy_die(fn, "device allocation failed");
+    cudaError_t e = cudaMemcpyAsync(din, src0, px, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(din + px, src1, px / 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(din + px + px / 4, src2, px / 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cuda_fail(e, "H2D"); legacy_die(fn, "copy failed"); }
+    int r = geom_fast(width, height)
+                ? lv::launch_convert(lv::make_geom(width, height), din, 1, dout, st)
+                : lv::launch_convert_generic(width, height, din, din + px, din + px + px / 4, dout, st);
+    if (r < 0) { cuda_fail((cudaError_t)(-r), "launch"); legacy_die(fn, "kernel launch failed"); }
+    e = cudaMemcpyAsync(dst_ori, dout, 3 * px, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cuda_fail(e, "D2H"); legacy_die(fn, "copy failed"); }
+}
+
+void FrameDiff_MB(const unsigned char *cur_y, const unsigned char *ref_y, int width, int height, int tol, int mb_thresh,
+                  unsigned char *mask, unsigned short *mb_count, unsigned char *mb_map)
+{
+    static const char *fn = "FrameDiff_MB";
+    if (!cur_y || !ref_y) legacy_die(fn, "NULL plane");
+    if (width <= 0 || height <= 0) return;
+    if (tol < 0) tol = -1;          // IsNearlyZero(a, tol<0) is never true except ... nothing: every pixel changed
+    if (tol > 255) tol = 255;
+    cudaStream_t st = legacy_stream(fn);
+    const size_t px = (size_t)width * height;
+    const int mb_w = (width + 15) / 16, mb_h = (height + 15) / 16;
+    const size_t mbs = (size_t)mb_w * mb_h;
+    // layout of the output scratch: mask bytes | counts (u16, 2-byte aligned) | map
+    const size_t off_cnt = (px + 15) & ~(size_t)15, off_map = off_cnt + ((2 * mbs + 15) & ~(size_t)15);
+    uint8_t *din = t_in.get(2 * ((px + 15) & ~(size_t)15)), *dout = t_out.get(off_map + mbs);
+    if (!din || !dout) legacy_die(fn, "device allocation failed");
+    uint8_t *dref = din + ((px + 15) & ~(size_t)15);
+    cudaError_t e = cudaMemcpyAsync(din, cur_y, px, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dref, ref_y, px, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cuda_fail(e, "H2D"); legacy_die(fn, "copy failed"); }
+    uint8_t *dmask = mask ? dout : nullptr;
+    uint16_t *dcnt = reinterpret_cast<uint16_t *>(dout + off_cnt);
+    uint8_t *dmap = dout + off_map;
+    int r;
+    if (geom_fast(width, height) && tol >= 0) {
+        lv::DiffArgs a{};
+        a.g = lv::make_geom(width, height); a.cur_y = din; a.ref_y = dref; a.n_frames = 1;
+        a.tol = tol; a.mb_thresh = mb_thresh; a.mask_bytes = dmask; a.mb_count = dcnt; a.mb_map = dmap;
+        r = lv::launch_diff(a, st);
+    } else {
+        r = lv::launch_diff_generic(width, height, din, dref, tol, mb_thresh, dmask, dcnt, dmap, st);
+    }
+    if (r < 0) { cuda_fail((cudaError_t)(-r), "launch"); legacy_die(fn, "kernel launch failed"); }
+    if (mask && e == cudaSuccess) e = cudaMemcpyAsync(mask, dmask, px, cudaMemcpyDeviceToHost, st);
+    if (mb_count && e == cudaSuccess) e = cudaMemcpyAsync(mb_count, dcnt, 2 * mbs, cudaMemcpyDeviceToHost, st);
+    if (mb_map && e == cudaSuccess) e = cudaMemcpyAsync(mb_map, dmap, mbs, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cuda_fail(e, "D2H"); legacy_die(fn, "copy failed"); }
+}
+
+}  // extern "C"

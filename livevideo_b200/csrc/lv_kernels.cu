@@ -1,0 +1,264 @@
+// lv_kernels.cu -- sm_100a kernels of the fused YUV420 -> BGR24 + frame-difference hot path.
+//
+// K1 k_tile<true,true>   fused conversion + difference + per-macroblock counts/map (+ masks, summary)
+// K2 k_tile<true,false>  conversion only  (ColorSpaceConversions::YV12_to_RGB24, Convert.h:26)
+// K3 k_tile<false,true>  difference only  (IsNearlyZero loops, lib/JM/image.c:4791-4804)
+//
+// Work decomposition (all three): one thread owns a 16-pixel x 2-row patch, i.e. one 16-byte luma
+// load per row, one 8-byte load of U and of V (the 2x2 chroma replication of the reference stays in
+// registers), one 16-byte load per row of the reference luma, and 3 x 16-byte BGR stores per row.
+// A block is 32 x 8 such threads = 512 pixels x 16 rows = 32 macroblocks of one macroblock row
+// (k = mby*mb_w + mbx, lib/JM/image.c:4981); the 8 row-pair partial counts of a macroblock are
+// summed through shared memory, so mb_count/mb_map need no atomics.  grid = (x tiles, mb rows,
+// frames) with the frame index slowest, so frame t-1's luma (read as "current" a moment ago) is
+// still in L2 when frame t reads it as the reference.
+#include "lv_kernels.h"
+#include "lv_pixel.cuh"
+
+namespace lv {
+
+namespace {
+
+struct KArgs {
+    Geom g;
+    const uint8_t *y0;          // luma of frame 0
+    size_t y_stride;            // bytes between consecutive frames' luma (frame for I420, px for planes)
+    const uint8_t *ref_planes;  // K3: explicit reference planes (stride px); else NULL
+    const uint8_t *state_in;    // K1: carried previous luma, one plane per stream
+    uint8_t *state_out;
+    int n_frames;               // frames per stream (t = f % n_frames)
+    int f_base;                 // first frame index of this launch (gridDim.z is limited to 65535)
+    int tol, mb_thresh;
+    uint8_t *bgr;
+    uint16_t *mask_bits;
+    uint8_t *mask_bytes;
+    uint16_t *mb_count;
+    uint8_t *mb_map;
+    uint32_t *summary;
+};
+
+__device__ __forceinline__ uint4 ld16(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ uint4 ld16_stream(const uint8_t *p) { return __ldcs(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ uint2 ld8_stream(const uint8_t *p) { return __ldcs(reinterpret_cast<const uint2 *>(p)); }
+__device__ __forceinline__ void st16_stream(uint8_t *p, const uint4 &v) { __stcs(reinterpret_cast<uint4 *>(p), v); }
+
+// 16 pixels of one row: luma words yw[4], chroma samples c[8] -> 48 bytes
+__device__ __forceinline__ void convert_row16(const uint4 &y, const Chroma2 (&c)[8], uint8_t *dst)
+{
+    uint4 o0, o1, o2;
+    convert4(y.x, c[0], c[1], o0.x, o0.y, o0.z);
+    convert4(y.y, c[2], c[3], o0.w, o1.x, o1.y);
+    convert4(y.z, c[4], c[5], o1.z, o1.w, o2.x);
+    convert4(y.w, c[6], c[7], o2.y, o2.z, o2.w);
+    st16_stream(dst, o0);
+    st16_stream(dst + 16, o1);
+    st16_stream(dst + 32, o2);
+}
+
+template <bool kConv, bool kDiff>
+__global__ void __launch_bounds__(256) k_tile(const KArgs a)
+{
+    const Geom &g = a.g;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int unit = blockIdx.x * 32 + tx;
+    const int row0 = blockIdx.y * 16 + 2 * ty;
+    const int f = a.f_base + blockIdx.z;
+    const bool active = unit < g.units && row0 < g.h;
+
+    uint32_t cnt = 0;
+    if (active) {
+        const uint8_t *yf = a.y0 + (size_t)f * a.y_stride;
+        const size_t off = (size_t)row0 * g.w + (size_t)unit * 16;
+        const uint4 y0 = ld16(yf + off);
+        const uint4 y1 = ld16(yf + off + g.w);
+
+        if constexpr (kDiff) {
+            const int t = f % a.n_frames;
+            const uint8_t *ref;
+            if (a.ref_planes) ref = a.ref_planes + (size_t)f * g.px;
+            else if (t == 0) ref = a.state_in + (size_t)(f / a.n_frames) * g.px;
+            else ref = yf - a.y_stride;
+            const uint4 p0 = ld16_stream(ref + off);
+            const uint4 p1 = ld16_stream(ref + off + g.w);
+            const uint32_t tol4 = (uint32_t)a.tol * 0x01010101u;
+            const uint32_t ntol7 = ~tol4 & 0x7f7f7f7fu;
+            const uint32_t m0 = diff_mask16(y0, p0, tol4, ntol7);
+            const uint32_t m1 = diff_mask16(y1, p1, tol4, ntol7);
+            cnt = __popc(m0) + __popc(m1);
+            if (a.mask_bits) {
+                uint16_t *mb = a.mask_bits + ((size_t)f * g.h + row0) * g.units + unit;
+                mb[0] = (uint16_t)m0;
+                mb[g.units] = (uint16_t)m1;
+            }
+            if (a.mask_bytes) {
+                uint8_t *mp = a.mask_bytes + (size_t)f * g.px + off;
+                st16_stream(mp, make_uint4(mask_bytes4(m0, 0), mask_bytes4(m0, 1), mask_bytes4(m0, 2), mask_bytes4(m0, 3)));
+                st16_stream(mp + g.w, make_uint4(mask_bytes4(m1, 0), mask_bytes4(m1, 1), mask_bytes4(m1, 2), mask_bytes4(m1, 3)));
+            }
+            if (a.state_out && t == a.n_frames - 1) {
+                // prev_frm <- curr_frm (lib/JM/image.c:1553-1561): the last frame becomes the state
+                uint8_t *so = a.state_out + (size_t)(f / a.n_frames) * g.px + off;
+                *reinterpret_cast<uint4 *>(so) = y0;
+                *reinterpret_cast<uint4 *>(so + g.w) = y1;
+            }
+        }
+
+        if constexpr (kConv) {
+            const uint8_t *uf = yf + g.px;
+            const size_t coff = (size_t)(row0 >> 1) * (g.w >> 1) + (size_t)unit * 8;
+            const uint2 u = ld8_stream(uf + coff);
+            const uint2 v = ld8_stream(uf + (g.px >> 2) + coff);
+            Chroma2 c[8];
+            c[0] = chroma_terms(ubyte<0>(u.x), ubyte<0>(v.x));
+            c[1] = chroma_terms(ubyte<1>(u.x), ubyte<1>(v.x));
+            c[2] = chroma_terms(ubyte<2>(u.x), ubyte<2>(v.x));
+            c[3] = chroma_terms(ubyte<3>(u.x), ubyte<3>(v.x));
+            c[4] = chroma_terms(ubyte<0>(u.y), ubyte<0>(v.y));
+            c[5] = chroma_terms(ubyte<1>(u.y), ubyte<1>(v.y));
+            c[6] = chroma_terms(ubyte<2>(u.y), ubyte<2>(v.y));
+            c[7] = chroma_terms(ubyte<3>(u.y), ubyte<3>(v.y));
+            // bottom-up DIB: source row r lands in destination row h-1-r (Convert.obj .text+0x350..0x39f)
+            uint8_t *d0 = a.bgr + (size_t)f * 3 * g.px + (size_t)(g.h - 1 - row0) * 3 * g.w + (size_t)unit * 48;
+            convert_row16(y0, c, d0);
+            convert_row16(y1, c, d0 - (size_t)3 * g.w);
+        }
+    }
+
+    if constexpr (kDiff) {
+        __shared__ uint32_t part[8][32];
+        part[ty][tx] = cnt;
+        __syncthreads();
+        if (ty == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) tot += part[i][tx];
+            const bool valid = unit < g.units;
+            const uint32_t on = valid && (int)tot > a.mb_thresh;
+            if (valid) {
+                const size_t k = (size_t)f * g.mb_w * g.mb_h + (size_t)blockIdx.y * g.mb_w + unit;
+                if (a.mb_count) a.mb_count[k] = (uint16_t)tot;
+                if (a.mb_map) a.mb_map[k] = (uint8_t)on;
+            }
+            if (a.summary) {
+                uint32_t spx = valid ? tot : 0, smb = on;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    spx += __shfl_xor_sync(0xffffffffu, spx, o);
+                    smb += __shfl_xor_sync(0xffffffffu, smb, o);
+                }
+                if (tx == 0) {
+                    if (spx) atomicAdd(a.summary + 2 * (size_t)f, spx);
+                    if (smb) atomicAdd(a.summary + 2 * (size_t)f + 1, smb);
+                }
+            }
+        }
+    }
+}
+
+template <bool kConv, bool kDiff>
+int launch_tile(const KArgs &a, int total_frames, cudaStream_t st)
+{
+    if (total_frames <= 0) return 0;
+    int launches = 0;
+    for (int f0 = 0; f0 < total_frames; f0 += 65535) {   // gridDim.z <= 65535
+        const int nf = total_frames - f0 < 65535 ? total_frames - f0 : 65535;
+        KArgs b = a;
+        b.f_base = f0;
+        dim3 grid((a.g.units + 31) / 32, a.g.mb_h, nf), block(32, 8);
+        k_tile<kConv, kDiff><<<grid, block, 0, st>>>(b);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return -(int)e;
+        launches++;
+    }
+    return launches;
+}
+
+// ---- generic geometry (width % 4 == 0, not a multiple of 16): one thread per 2x2 quad ------------
+__global__ void k_convert_generic(int w, int h, const uint8_t *__restrict__ y, const uint8_t *__restrict__ u,
+                                  const uint8_t *__restrict__ v, uint8_t *__restrict__ bgr)
+{
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (cx >= (w >> 1) || cy >= (h >> 1)) return;
+    const Chroma2 c = chroma_terms(u[(size_t)cy * (w >> 1) + cx], v[(size_t)cy * (w >> 1) + cx]);
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int row = 2 * cy + r;
+        const uint8_t *yp = y + (size_t)row * w + 2 * cx;
+        const uint32_t t2 = luma_pair(yp[0], yp[1]);
+        const uint32_t B = chan_pair(t2, c.cb2), G = chan_pair(t2, c.ng2), R = chan_pair(t2, c.cr2);
+        uint8_t *d = bgr + (size_t)(h - 1 - row) * 3 * w + 6 * cx;
+        d[0] = (uint8_t)B; d[1] = (uint8_t)G; d[2] = (uint8_t)R;
+        d[3] = (uint8_t)(B >> 16); d[4] = (uint8_t)(G >> 16); d[5] = (uint8_t)(R >> 16);
+    }
+}
+
+// one block (16x16 threads) per macroblock
+__global__ void k_diff_generic(int w, int h, const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref,
+                               int tol, int mb_thresh, uint8_t *mask, uint16_t *mb_count, uint8_t *mb_map)
+{
+    const int x = blockIdx.x * 16 + threadIdx.x, yy = blockIdx.y * 16 + threadIdx.y;
+    int m = 0;
+    if (x < w && yy < h) {
+        const int d = (int)cur[(size_t)yy * w + x] - (int)ref[(size_t)yy * w + x];
+        m = (d > tol) || (d < -tol);   // !IsNearlyZero(d, tol), lib/JM/image.h:22
+        if (mask) mask[(size_t)yy * w + x] = (uint8_t)m;
+    }
+    const int tot = __syncthreads_count(m);
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const size_t k = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        if (mb_count) mb_count[k] = (uint16_t)tot;
+        if (mb_map) mb_map[k] = (uint8_t)(tot > mb_thresh);
+    }
+}
+
+}  // namespace
+
+int launch_step(const StepArgs &s, cudaStream_t st)
+{
+    KArgs a{};
+    a.g = s.g; a.y0 = s.i420; a.y_stride = s.g.frame; a.ref_planes = nullptr;
+    a.state_in = s.state_in; a.state_out = s.state_out; a.n_frames = s.n_frames;
+    a.tol = s.tol; a.mb_thresh = s.mb_thresh;
+    a.bgr = s.bgr; a.mask_bits = s.mask_bits; a.mask_bytes = s.mask_bytes;
+    a.mb_count = s.mb_count; a.mb_map = s.mb_map; a.summary = s.summary;
+    const int total = s.n_streams * s.n_frames;
+    return s.bgr ? launch_tile<true, true>(a, total, st) : launch_tile<false, true>(a, total, st);
+}
+
+int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st)
+{
+    KArgs a{};
+    a.g = g; a.y0 = i420; a.y_stride = g.frame; a.n_frames = n_frames > 0 ? n_frames : 1; a.bgr = bgr;
+    return launch_tile<true, false>(a, n_frames, st);
+}
+
+int launch_diff(const DiffArgs &d, cudaStream_t st)
+{
+    KArgs a{};
+    a.g = d.g; a.y0 = d.cur_y; a.y_stride = d.g.px; a.ref_planes = d.ref_y; a.n_frames = 1;
+    a.tol = d.tol; a.mb_thresh = d.mb_thresh;
+    a.mask_bits = d.mask_bits; a.mask_bytes = d.mask_bytes; a.mb_count = d.mb_count; a.mb_map = d.mb_map;
+    a.summary = d.summary;
+    return launch_tile<false, true>(a, d.n_frames, st);
+}
+
+int launch_convert_generic(int w, int h, const uint8_t *y, const uint8_t *u, const uint8_t *v, uint8_t *bgr,
+                           cudaStream_t st)
+{
+    dim3 block(32, 8), grid(((w >> 1) + 31) / 32, ((h >> 1) + 7) / 8);
+    k_convert_generic<<<grid, block, 0, st>>>(w, h, y, u, v, bgr);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+int launch_diff_generic(int w, int h, const uint8_t *cur, const uint8_t *ref, int tol, int mb_thresh,
+                        uint8_t *mask_bytes, uint16_t *mb_count, uint8_t *mb_map, cudaStream_t st)
+{
+    dim3 block(16, 16), grid((w + 15) / 16, (h + 15) / 16);
+    k_diff_generic<<<grid, block, 0, st>>>(w, h, cur, ref, tol, mb_thresh, mask_bytes, mb_count, mb_map);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+}  // namespace lv

@@ -1,0 +1,67 @@
+// lv_kernels.h -- internal launch interface between the C ABI (lv_capi.cu) and the kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lv {
+
+struct Geom {
+    int w, h;          // pixels
+    int units;         // w / 16 (16-pixel column units)
+    int mb_w, mb_h;    // ceil(w/16), ceil(h/16)   (lib/JM/image.c:4677-4679 uses floor on MB-aligned sizes)
+    size_t px;         // w*h
+    size_t frame;      // 1.5*w*h, bytes of one I420 frame
+};
+
+inline Geom make_geom(int w, int h)
+{
+    Geom g;
+    g.w = w; g.h = h; g.units = w / 16;
+    g.mb_w = (w + 15) / 16; g.mb_h = (h + 15) / 16;
+    g.px = (size_t)w * h; g.frame = g.px + g.px / 2;
+    return g;
+}
+
+// One launch of the fused step over n_streams*n_frames frames (stream-major).
+struct StepArgs {
+    Geom g;
+    const uint8_t *i420;      // input frames
+    const uint8_t *state_in;  // previous luma planes, n_streams x px (slot of stream s = s)
+    uint8_t *state_out;       // luma of the last frame of each stream is written here (may be NULL)
+    int n_streams, n_frames;
+    int tol, mb_thresh;
+    uint8_t *bgr;             // any output may be NULL
+    uint16_t *mask_bits;
+    uint8_t *mask_bytes;
+    uint16_t *mb_count;
+    uint8_t *mb_map;
+    uint32_t *summary;        // 2 per frame; must be zeroed before the launch
+};
+
+// difference of explicit (cur, ref) plane pairs: frame i of cur_y against frame i of ref_y
+struct DiffArgs {
+    Geom g;
+    const uint8_t *cur_y, *ref_y;
+    int n_frames;
+    int tol, mb_thresh;
+    uint16_t *mask_bits;
+    uint8_t *mask_bytes;
+    uint16_t *mb_count;
+    uint8_t *mb_map;
+    uint32_t *summary;
+};
+
+// width % 16 == 0, height % 2 == 0.  Return the number of kernels launched (>0) or a negative
+// cudaError_t value (-(int)err).
+int launch_step(const StepArgs &a, cudaStream_t st);
+int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st);
+int launch_diff(const DiffArgs &a, cudaStream_t st);
+
+// any width % 4 == 0 / height % 2 == 0 (legacy geometry that is not a multiple of 16)
+int launch_convert_generic(int w, int h, const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                           uint8_t *bgr, cudaStream_t st);
+int launch_diff_generic(int w, int h, const uint8_t *cur, const uint8_t *ref, int tol, int mb_thresh,
+                        uint8_t *mask_bytes, uint16_t *mb_count, uint8_t *mb_map, cudaStream_t st);
+
+}  // namespace lv

@@ -1,0 +1,116 @@
+// lv_pixel.cuh -- per-pixel arithmetic of the hot path, written for sm_100a integer SIMD.
+//
+// Colour conversion: bit-exact with ColorSpaceConversions::YV12_to_RGB24 of the reference
+// (Convert.h:26; code in cscc.lib, Convert.obj .text+0x350, tables built at .text+0x110..0x1c1):
+//     t  = (76309*(Y-16))  >> 15                       tab_76309
+//     cb = (132201*(U-128)) >> 15                      cbu_tab
+//     cr = (104597*(V-128)) >> 15                      crv_tab
+//     g  = (25675*(U-128) + 53279*(V-128)) >> 15       cgu_tab + cgv_tab, ONE shift of the sum
+//     B = clp(t + cb), G = clp(t - g), R = clp(t + cr),  clp(x) = x<0 ? 0 : x>510 ? 255 : x>>1
+// (all shifts arithmetic).  No tables on the GPU: every term is one IMAD whose multiplier is
+// doubled so the wanted value is the upper halfword (x>>15 == (2x)>>16), two pixels are packed per
+// register as s16x2 with PRMT, and add+clamp is one VIADDMNMX.S16x2.RELU (DPX) per channel per
+// pixel pair:  clp(x) == min(max(x,0),511) >> 1.
+//   -g is formed directly: -floor(s/2^15) == floor((-s + 32767)/2^15).
+//
+// Difference: IsNearlyZero (lib/JM/image.h:22) => changed <=> |cur - ref| > tol, on 4 pixels per
+// 32-bit lane with VABSDIFF4 and a carry trick for the per-byte compare.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lv {
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    return __byte_perm(a, b, sel);
+}
+
+// byte k (0..3) of w, zero extended
+template <int K>
+__device__ __forceinline__ int ubyte(uint32_t w)
+{
+    return (int)prmt(w, 0u, 0x4440u | (uint32_t)K);
+}
+
+// Chroma terms of one (U,V) sample, each duplicated into both halfwords (the two pixels of a
+// horizontal pair share the sample; so do the two rows).
+struct Chroma2 {
+    uint32_t cb2, ng2, cr2;
+};
+
+__device__ __forceinline__ Chroma2 chroma_terms(int u, int v)
+{
+    // doubled multipliers: the result of interest is the upper halfword
+    const int CB = u * (2 * 132201) - (2 * 132201) * 128;
+    const int CR = v * (2 * 104597) - (2 * 104597) * 128;
+    const int NG = u * (-2 * 25675) + (v * (-2 * 53279) + ((2 * 25675 + 2 * 53279) * 128 + 2 * 32767));
+    Chroma2 c;
+    c.cb2 = prmt((uint32_t)CB, 0u, 0x3232u);
+    c.cr2 = prmt((uint32_t)CR, 0u, 0x3232u);
+    c.ng2 = prmt((uint32_t)NG, 0u, 0x3232u);
+    return c;
+}
+
+// luma terms of two horizontally adjacent pixels packed as s16x2 (low half = even pixel)
+__device__ __forceinline__ uint32_t luma_pair(int ya, int yb)
+{
+    const int TA = ya * (2 * 76309) - (2 * 76309) * 16;
+    const int TB = yb * (2 * 76309) - (2 * 76309) * 16;
+    return prmt((uint32_t)TA, (uint32_t)TB, 0x7632u);
+}
+
+// add + clamp to [0,511] per halfword, then >>1: low byte of each halfword is the channel value
+// (bit 15 of the low halfword may carry garbage from the upper one; it is never selected).
+__device__ __forceinline__ uint32_t chan_pair(uint32_t t2, uint32_t c2)
+{
+    return __viaddmin_s16x2_relu(t2, c2, 0x01ff01ffu) >> 1;
+}
+
+// 4 pixels (one 32-bit word of luma, two chroma samples) -> 12 bytes B,G,R,B,G,R,...
+__device__ __forceinline__ void convert4(uint32_t yw, const Chroma2 &c0, const Chroma2 &c1,
+                                         uint32_t &o0, uint32_t &o1, uint32_t &o2)
+{
+    const uint32_t ta = luma_pair(ubyte<0>(yw), ubyte<1>(yw));
+    const uint32_t tb = luma_pair(ubyte<2>(yw), ubyte<3>(yw));
+    const uint32_t Ba = chan_pair(ta, c0.cb2), Ga = chan_pair(ta, c0.ng2), Ra = chan_pair(ta, c0.cr2);
+    const uint32_t Bb = chan_pair(tb, c1.cb2), Gb = chan_pair(tb, c1.ng2), Rb = chan_pair(tb, c1.cr2);
+    // pixel p of pair x sits in byte 0 (even) / byte 2 (odd) of Bx,Gx,Rx
+    o0 = prmt(prmt(Ba, Ga, 0x2040u), Ra, 0x3410u);                       // b0 g0 r0 b1
+    o1 = prmt(prmt(prmt(Ga, Ra, 0x0062u), Bb, 0x0410u), Gb, 0x4210u);    // g1 r1 b2 g2
+    o2 = prmt(prmt(Rb, Bb, 0x2060u), Gb, 0x3610u);                       // r2 b3 g3 r3
+}
+
+// per-byte (|a-b| > tol) for 4 pixels: returns a word whose bit 7 of byte k is the result for
+// pixel k (other bits undefined).  ntol7 = (~tol4) & 0x7f7f7f7f, tol4 = tol * 0x01010101.
+__device__ __forceinline__ uint32_t diff_gt4(uint32_t a, uint32_t b, uint32_t tol4, uint32_t ntol7)
+{
+    const uint32_t d = __vabsdiffu4(a, b);
+    // d > tol per byte without cross-byte carries: add the low 7 bits, then resolve bit 7 with a
+    // majority-style LOP3:  gt = (d & ~tol) | (~(d ^ tol) & carry)   evaluated on bit 7
+    const uint32_t s = (d & 0x7f7f7f7fu) + ntol7;
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xb2;" : "=r"(r) : "r"(d), "r"(tol4), "r"(s));
+    return r;
+}
+
+// 16 pixels -> 16-bit mask, bit i = pixel i changed
+__device__ __forceinline__ uint32_t diff_mask16(const uint4 &cur, const uint4 &ref, uint32_t tol4,
+                                                uint32_t ntol7)
+{
+    // gather bit 7 of each byte into a nibble: (x & 0x80808080) * 0x00204081 >> 28
+    const uint32_t g0 = (diff_gt4(cur.x, ref.x, tol4, ntol7) & 0x80808080u) * 0x00204081u >> 28;
+    const uint32_t g1 = (diff_gt4(cur.y, ref.y, tol4, ntol7) & 0x80808080u) * 0x00204081u >> 28;
+    const uint32_t g2 = (diff_gt4(cur.z, ref.z, tol4, ntol7) & 0x80808080u) * 0x00204081u >> 28;
+    const uint32_t g3 = (diff_gt4(cur.w, ref.w, tol4, ntol7) & 0x80808080u) * 0x00204081u >> 28;
+    return g0 | (g1 << 4) | (g2 << 8) | (g3 << 12);
+}
+
+// expand 4 mask bits (bits 4k..4k+3 of m) to 4 bytes of 0/1
+__device__ __forceinline__ uint32_t mask_bytes4(uint32_t m, int k)
+{
+    const uint32_t n = (m >> (4 * k)) & 0xfu;
+    return (n * 0x00204081u) & 0x01010101u;
+}
+
+}  // namespace lv
