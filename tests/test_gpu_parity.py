@@ -1,0 +1,382 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (run on the B200 box: -m gpu).
+
+Bar: bit-exact for every output -- BGR bytes, difference masks (bytes and bits), per-macroblock counts, the
+block map, the per-frame summaries and the carried previous-luma state."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def run_fused(lv, torch, frames, ns, nf, w, h, tol, thr, ctx=None, masks=True):
+    own = ctx is None
+    ctx = ctx or lv.Context(w, h, ns, tol, thr)
+    d_in = torch.from_numpy(np.ascontiguousarray(frames).reshape(-1)).cuda()
+    out = ctx.alloc_outputs(ns * nf, mask_bits=masks, mask_bytes=masks)
+    ctx.convert_diff_batch(d_in, ns, nf, out)
+    torch.cuda.synchronize()
+    res = {k: (None if v is None else v.cpu().numpy()) for k, v in out.items()}
+    res["mb_count"] = res["mb_count"].view(np.uint16)
+    res["summary"] = res["summary"].view(np.uint32).reshape(-1, 2)
+    if masks:
+        res["mask_bits"] = res["mask_bits"].view(np.uint16)
+    if own:
+        res["state"] = np.stack([ctx.get_prev_luma(s) for s in range(ns)])
+        ctx.close()
+    return res
+
+
+def assert_matches_oracle(orc, got, ref, w, h, n, masks=True):
+    assert np.array_equal(got["bgr"], ref["bgr"]), "BGR bytes differ"
+    assert np.array_equal(got["mb_count"], ref["mb_count"]), "macroblock counts differ"
+    assert np.array_equal(got["mb_map"], ref["mb_map"]), "block map differs"
+    assert np.array_equal(got["summary"], ref["summary"]), "summaries differ"
+    if masks:
+        assert np.array_equal(got["mask_bytes"], ref["mask"]), "byte mask differs"
+        px = w * h
+        bits = np.concatenate([orc.pack_mask16(ref["mask"][i * px:(i + 1) * px], w, h) for i in range(n)])
+        assert np.array_equal(got["mask_bits"], bits), "bit mask differs"
+
+
+# ---- conversion -------------------------------------------------------------------------------------------
+
+def test_convert_exhaustive_2_24(lv, orc, torch_cuda):
+    """Every (Y,U,V) triple: 256 frames of 512x512 (Y constant per frame, U = column, V = row)."""
+    torch = torch_cuda
+    u = np.repeat(np.arange(256, dtype=np.uint8)[None, :], 256, 0).ravel()
+    v = np.repeat(np.arange(256, dtype=np.uint8)[:, None], 256, 1).ravel()
+    ctx = lv.Context(512, 512)
+    bad = 0
+    for y0 in range(0, 256, 64):
+        frames = np.stack([np.concatenate([np.full(512 * 512, y, np.uint8), u, v]) for y in range(y0, y0 + 64)])
+        d_in = torch.from_numpy(frames.reshape(-1)).cuda()
+        d_out = torch.empty(64 * ctx.bgr_bytes, dtype=torch.uint8, device="cuda")
+        ctx.convert_batch(d_in, 64, d_out)
+        got = d_out.cpu().numpy().reshape(64, -1)
+        for i in range(64):
+            bad += int((got[i] != orc.convert_frame(frames[i], 512, 512)).sum())
+    assert bad == 0
+
+
+def test_convert_golden_digests_device_and_legacy_entry(lv, orc, golden, torch_cuda):
+    """Digests recorded from the reference's original object code (tests/golden + SURVEY.md 8(c))."""
+    torch = torch_cuda
+    csc = lv.ColorSpaceConversions()
+    for e in golden["convert"]:
+        w, h = e["w"], e["h"]
+        fr = orc.gen(e["kind"], e["seed"], e["stream"], e["frame"], w, h)
+        px = w * h
+        dst = np.zeros(3 * px, dtype=np.uint8)
+        csc.YV12_to_RGB24(fr[:px].copy(), fr[px:px + px // 4].copy(), fr[px + px // 4:].copy(), dst, w, h)
+        assert dst[:6].tolist() == e["first6"], e
+        assert sha(dst) == e["sha256"], ("legacy entry", e)
+        if w % 16 == 0:
+            ctx = lv.Context(w, h)
+            d_out = torch.empty(ctx.bgr_bytes, dtype=torch.uint8, device="cuda")
+            ctx.convert_batch(torch.from_numpy(fr).cuda(), 1, d_out)
+            assert sha(d_out.cpu().numpy()) == e["sha256"], ("device entry", e)
+            ctx.close()
+
+
+def test_legacy_kats_and_layout(lv, golden, torch_cuda):
+    csc = lv.ColorSpaceConversions()
+    for k in golden["kat"]:
+        y, u, v = k["yuv"]
+        dst = np.zeros(24, np.uint8)
+        csc.YV12_to_RGB24(np.full(8, y, np.uint8), np.full(2, u, np.uint8), np.full(2, v, np.uint8), dst, 4, 2)
+        assert dst.reshape(8, 3).tolist() == [k["bgr"]] * 8
+    y = np.repeat(np.array([16, 80, 160, 235], dtype=np.uint8), 4)
+    dst = np.zeros(48, np.uint8)
+    csc.YV12_to_RGB24(y, np.full(4, 128, np.uint8), np.full(4, 128, np.uint8), dst, 4, 4)
+    assert [int(dst[12 * r]) for r in range(4)] == golden["layout_kat"]["first_byte_of_dst_rows"]   # bottom-up
+    dst = np.zeros(24, np.uint8)
+    csc.YV12_to_RGB24(np.full(8, 128, np.uint8), np.array([0, 255], np.uint8), np.full(2, 128, np.uint8), dst, 4, 2)
+    assert [int(dst[3 * p]) for p in range(4)] == golden["chroma_kat"]["b_row0"]                     # 2x2 replication
+    assert [int(dst[12 + 3 * p]) for p in range(4)] == golden["chroma_kat"]["b_row1"]
+    with pytest.raises(ValueError):
+        csc.YV12_to_RGB24(np.zeros(6, np.uint8), np.zeros(2, np.uint8), np.zeros(2, np.uint8), np.zeros(18, np.uint8), 3, 2)
+    with pytest.raises(NotImplementedError):
+        csc.RGB24_to_YV12(None, None, 4, 2)
+
+
+@pytest.mark.parametrize("w,h", [(4, 2), (8, 2), (12, 10), (20, 6), (36, 4), (100, 50), (16, 2), (32, 18), (528, 34)])
+def test_legacy_convert_odd_geometries(lv, orc, torch_cuda, w, h):
+    rng = np.random.default_rng(w * 1000 + h)
+    px = w * h
+    fr = rng.integers(0, 256, px * 3 // 2, dtype=np.uint8)
+    dst = np.zeros(3 * px, np.uint8)
+    lv.ColorSpaceConversions().YV12_to_RGB24(fr[:px].copy(), fr[px:px + px // 4].copy(), fr[px + px // 4:].copy(),
+                                             dst, w, h)
+    assert np.array_equal(dst, orc.convert_frame(fr, w, h))
+
+
+# ---- fused step ----------------------------------------------------------------------------------------------
+
+def test_fused_golden_entries(lv, orc, golden, torch_cuda):
+    for e in golden["diff"]:
+        w, h, ns, nf = e["w"], e["h"], e["n_streams"], e["n_frames"]
+        frames = orc.gen_batch(e["kind"], e["seed"], ns, nf, w, h)
+        got = run_fused(lv, torch_cuda, frames, ns, nf, w, h, e["tol"], e["mb_thresh"])
+        assert sha(got["bgr"]) == e["bgr"]["sha256"], e
+        assert sha(got["mask_bytes"]) == e["mask"]["sha256"], e
+        assert sha(got["mb_count"]) == e["mb_count"]["sha256"], e
+        assert sha(got["mb_map"]) == e["mb_map"]["sha256"], e
+        assert got["summary"].tolist() == e["summary"], e
+        assert sha(got["state"]) == e["state"]["sha256"], e
+
+
+@pytest.mark.parametrize("tol", [0, 1, 20, 25, 254, 255])
+@pytest.mark.parametrize("thr", [0, 1, 128, 255, 256])
+def test_fused_threshold_sweep(lv, orc, torch_cuda, tol, thr):
+    w, h, ns, nf = 176, 72, 2, 3          # 72 rows: partial last macroblock row (8 lines), like 1080
+    rng = np.random.default_rng(tol * 1000 + thr)
+    frames = rng.integers(0, 256, (ns, nf, w * h * 3 // 2), dtype=np.uint8)
+    # force many |d| in {tol, tol+1} and whole macroblocks at exactly 0 / 256 changed pixels
+    base = frames[:, 0, :w * h].astype(int)
+    frames[:, 1, :w * h:2] = np.clip(base[:, ::2] + tol, 0, 255)
+    frames[:, 1, 1:w * h:2] = np.clip(base[:, 1::2] - tol - 1, 0, 255)
+    frames[:, 2, :16 * w] = frames[:, 1, :16 * w]                 # first MB row unchanged
+    prev = np.zeros((ns, w * h), np.uint8)
+    ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, tol, thr)
+    got = run_fused(lv, torch_cuda, frames, ns, nf, w, h, tol, thr)
+    assert_matches_oracle(orc, got, ref, w, h, ns * nf)
+    assert np.array_equal(got["state"], prev)
+
+
+def test_fused_ragged_widths_and_tiny_frames(lv, orc, torch_cuda):
+    # widths that do not fill a 512-pixel block tile, heights with 1..8 row pairs in the last MB row
+    for (w, h) in [(16, 2), (16, 16), (48, 18), (528, 20), (1040, 30), (4112, 2)]:
+        frames = orc.gen_batch("camera" if h >= 16 and w >= 16 and h // 8 > 0 and w // 8 > 0 and w > w // 8 else "uniform",
+                               3, 2, 2, w, h) if h >= 16 else orc.gen_batch("uniform", 3, 2, 2, w, h)
+        prev = np.zeros((2, w * h), np.uint8)
+        ref = orc.convert_diff_batch(frames, prev, 2, 2, w, h, 20, 0)
+        got = run_fused(lv, torch_cuda, frames, 2, 2, w, h, 20, 0)
+        assert_matches_oracle(orc, got, ref, w, h, 4)
+
+
+def test_state_carry_split_batches_and_stream_ranges(lv, orc, torch_cuda):
+    torch = torch_cuda
+    w, h, ns, nf = 352, 288, 3, 6
+    frames = orc.gen_batch("camera", 7, ns, nf, w, h)
+    prev = np.zeros((ns, w * h), np.uint8)
+    ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, 20, 0)
+    # (a) two launches of 3 frames == one launch of 6 (the state carries frame 2's luma)
+    ctx = lv.Context(w, h, ns, 20, 0)
+    a = run_fused(lv, torch, frames[:, :3], ns, 3, w, h, 20, 0, ctx=ctx)
+    b = run_fused(lv, torch, frames[:, 3:], ns, 3, w, h, 20, 0, ctx=ctx)
+    cnt = np.concatenate([a["mb_count"].reshape(ns, 3, -1), b["mb_count"].reshape(ns, 3, -1)], axis=1)
+    assert np.array_equal(cnt.reshape(-1), ref["mb_count"])
+    bgr = np.concatenate([a["bgr"].reshape(ns, 3, -1), b["bgr"].reshape(ns, 3, -1)], axis=1)
+    assert np.array_equal(bgr.reshape(-1), ref["bgr"])
+    for s in range(ns):
+        assert np.array_equal(ctx.get_prev_luma(s), prev[s])
+    ctx.close()
+    # (b) stepping only stream 1 leaves the state of streams 0 and 2 alone
+    ctx = lv.Context(w, h, ns, 20, 0)
+    for s in range(ns):
+        ctx.set_prev_luma(s, frames[s, 0, :w * h].copy())
+    out = ctx.alloc_outputs(2)
+    ctx.convert_diff_batch(torch.from_numpy(frames[1, 1:3].reshape(-1).copy()).cuda(), 1, 2, out, first_stream=1)
+    torch.cuda.synchronize()
+    assert np.array_equal(ctx.get_prev_luma(0), frames[0, 0, :w * h])
+    assert np.array_equal(ctx.get_prev_luma(2), frames[2, 0, :w * h])
+    assert np.array_equal(ctx.get_prev_luma(1), frames[1, 2, :w * h])
+    p1 = frames[1, 0, :w * h].copy().reshape(1, -1)
+    r1 = orc.convert_diff_batch(frames[1, 1:3], p1, 1, 2, w, h, 20, 0)
+    assert np.array_equal(out["mb_count"].cpu().numpy().view(np.uint16), r1["mb_count"])
+    # (c) static background as the reference (MainDlg.cpp:238-246): reset + set
+    ctx.reset_prev_luma()
+    torch.cuda.synchronize()
+    assert not ctx.get_prev_luma(1).any()
+    ctx.close()
+
+
+def test_identical_frames_and_idempotence(lv, orc, torch_cuda):
+    w, h = 352, 288
+    fr = orc.gen("camera", 2, 0, 0, w, h)
+    frames = np.stack([fr, fr, fr])[None]
+    got = run_fused(lv, torch_cuda, frames, 1, 3, w, h, 0, 0)
+    assert got["summary"][1:].tolist() == [[0, 0], [0, 0]]          # tol = 0: identical frames never change
+    assert not got["mask_bytes"][w * h:].any()
+    again = run_fused(lv, torch_cuda, frames, 1, 3, w, h, 0, 0)
+    for k in ("bgr", "mask_bytes", "mask_bits", "mb_count", "mb_map", "summary"):
+        assert np.array_equal(got[k], again[k])
+
+
+def test_diff_only_entry_and_legacy_framediff(lv, orc, torch_cuda):
+    torch = torch_cuda
+    rng = np.random.default_rng(5)
+    w, h, n = 352, 288, 3
+    cur = rng.integers(0, 256, (n, w * h), dtype=np.uint8)
+    ref = np.clip(cur.astype(int) + rng.integers(-30, 31, (n, w * h)), 0, 255).astype(np.uint8)
+    ctx = lv.Context(w, h, 1, 20, 3)
+    out = ctx.alloc_outputs(n, bgr=False, mask_bits=True, mask_bytes=True)
+    ctx.diff_batch(torch.from_numpy(cur.reshape(-1)).cuda(), torch.from_numpy(ref.reshape(-1)).cuda(), n, out)
+    torch.cuda.synchronize()
+    for i in range(n):
+        mask, cnt, mp, total = orc.frame_diff_mb(cur[i], ref[i], w, h, 20, 3)
+        assert np.array_equal(out["mask_bytes"].cpu().numpy()[i * w * h:(i + 1) * w * h], mask)
+        assert np.array_equal(out["mb_count"].cpu().numpy().view(np.uint16)[i * ctx.mbs:(i + 1) * ctx.mbs], cnt)
+        assert np.array_equal(out["mb_map"].cpu().numpy()[i * ctx.mbs:(i + 1) * ctx.mbs], mp)
+        assert out["summary"].cpu().numpy().view(np.uint32)[2 * i] == total
+    ctx.close()
+    # the host-pointer legacy entry, incl. sizes that are not multiples of 16 and NULL outputs
+    for (w, h, tol, thr) in [(352, 288, 20, 0), (100, 50, 25, 10), (20, 6, 0, 0), (1920, 1080, 20, 128), (4, 2, 255, 0)]:
+        cur = rng.integers(0, 256, w * h, dtype=np.uint8)
+        ref = np.clip(cur.astype(int) + rng.integers(-40, 41, w * h), 0, 255).astype(np.uint8)
+        mask, cnt, mp = lv.FrameDiff_MB(cur, ref, w, h, tol, thr)
+        emask, ecnt, emp, _ = orc.frame_diff_mb(cur, ref, w, h, tol, thr)
+        assert np.array_equal(mask, emask) and np.array_equal(cnt, ecnt) and np.array_equal(mp, emp)
+    L = lv.lib()
+    cnt = np.zeros(396, np.uint16)
+    cur = rng.integers(0, 256, 352 * 288, dtype=np.uint8)
+    L.FrameDiff_MB(cur.ctypes.data, cur.ctypes.data, 352, 288, 20, 0, None, cnt.ctypes.data, None)   # NULL mask/map
+    assert not cnt.any()
+
+
+def test_host_step_equals_device_step(lv, orc, torch_cuda):
+    """lv_step_host (pinned, chunked, 3-slot pipeline) returns exactly what one device launch computes."""
+    w, h, ns, nf = 1280, 720, 5, 7            # > 32 MiB of input: several chunks, ragged last chunk
+    frames = orc.gen_batch("camera", 11, ns, nf, w, h)
+    prev = np.zeros((ns, w * h), np.uint8)
+    ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, 20, 0, want_mask=True, n_threads=4)
+    ctx = lv.Context(w, h, ns, 20, 0)
+    n = ns * nf
+    pin = lv.pinned(n * ctx.frame_bytes)
+    pin.array[:] = frames.reshape(-1)
+    bgr = lv.pinned(n * ctx.bgr_bytes)
+    bits = np.zeros(n * ctx.mask_units, np.uint16)
+    cnt = np.zeros(n * ctx.mbs, np.uint16)
+    mp = np.zeros(n * ctx.mbs, np.uint8)
+    summ = np.zeros(2 * n, np.uint32)
+    ctx.step_host(pin.array, ns, nf, bgr=bgr.array, mask_bits=bits, mb_count=cnt, mb_map=mp, summary=summ)
+    assert np.array_equal(bgr.array, ref["bgr"])
+    assert np.array_equal(cnt, ref["mb_count"]) and np.array_equal(mp, ref["mb_map"])
+    assert np.array_equal(summ.reshape(-1, 2), ref["summary"])
+    px = w * h
+    assert np.array_equal(bits, np.concatenate([orc.pack_mask16(ref["mask"][i * px:(i + 1) * px], w, h) for i in range(n)]))
+    for s in range(ns):
+        assert np.array_equal(ctx.get_prev_luma(s), prev[s])
+    # pageable host memory and a subset of outputs
+    summ2 = np.zeros(2 * n, np.uint32)
+    ctx.reset_prev_luma()
+    ctx.step_host(frames.reshape(-1).copy(), ns, nf, summary=summ2)
+    assert np.array_equal(summ2, summ)
+    ctx.close()
+
+
+def test_device_generator_matches_oracle_generator(lv, orc, torch_cuda):
+    for kind in ("uniform", "camera"):
+        d = lv.gen_synthetic(kind, 1, 2, 5, 2, 3, 352, 288)
+        torch_cuda.cuda.synchronize()
+        want = orc.gen_batch(kind, 1, 2, 3, 352, 288, first_frame=5, first_stream=2)
+        assert np.array_equal(d.cpu().numpy(), want.reshape(-1)), kind
+
+
+def test_errors_are_codes_not_crashes(lv, torch_cuda):
+    torch = torch_cuda
+    ctx = lv.Context(20, 6)                       # legal for the legacy entries, not for the batched kernels
+    buf = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    with pytest.raises(lv.LiveVideoError) as ei:
+        ctx.convert_batch(buf, 1, buf)
+    assert ei.value.code == -2
+    ctx.close()
+    ctx = lv.Context(352, 288, 2)
+    out = ctx.alloc_outputs(2)
+    d = torch.zeros(2 * ctx.frame_bytes, dtype=torch.uint8, device="cuda")
+    with pytest.raises(lv.LiveVideoError) as ei:
+        ctx.convert_diff_batch(d, 2, 1, out, first_stream=1)      # stream range exceeds max_streams
+    assert ei.value.code == -1
+    L = lv.lib()
+    assert L.lv_convert_diff_batch(ctx._h, None, 0, 1, 1, None, None, None, None, None, None, None) == -1
+    with pytest.raises(ValueError):
+        ctx.convert_batch(torch.zeros(10, dtype=torch.uint8, device="cuda"), 1, out["bgr"])       # too small
+    ctx.convert_diff_batch(d, 2, 0, out)          # empty batch: a no-op, not an error
+    ctx.close()
+    h = C.c_void_p()
+    assert L.lv_create(99, 352, 288, 1, 20, 0, C.byref(h)) == -3
+
+
+# ---- BASELINE.json configurations at full size --------------------------------------------------------------
+
+def _full_size(lv, orc, torch, w, h, ns, nf, kind="camera"):
+    n = ns * nf
+    ctx = lv.Context(w, h, ns, 20, 0)
+    d_in = lv.gen_synthetic(kind, 1, 0, 0, ns, nf, w, h)
+    out = ctx.alloc_outputs(n, mask_bits=True)
+    ctx.convert_diff_batch(d_in, ns, nf, out)
+    torch.cuda.synchronize()
+    frames = d_in.cpu().numpy().reshape(ns, nf, -1)
+    prev = np.zeros((ns, w * h), np.uint8)
+    import os
+    ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, 20, 0, want_mask=False,
+                                 n_threads=min(16, os.cpu_count() or 1))
+    cnt = out["mb_count"].cpu().numpy().view(np.uint16)
+    mp = out["mb_map"].cpu().numpy()
+    summ = out["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2)
+    assert np.array_equal(out["bgr"].cpu().numpy(), ref["bgr"])
+    assert np.array_equal(cnt, ref["mb_count"]) and np.array_equal(mp, ref["mb_map"])
+    assert np.array_equal(summ, ref["summary"])
+    # size-independent properties
+    assert np.array_equal(summ[:, 0], cnt.reshape(n, -1).sum(1))                  # checksum of checksums
+    assert np.array_equal(summ[:, 1], mp.reshape(n, -1).sum(1))
+    assert np.array_equal(mp, (cnt > 0).astype(np.uint8))
+    bits = out["mask_bits"].cpu().numpy().view(np.uint16)
+    pop = np.unpackbits(bits.view(np.uint8)).reshape(n, -1).sum(1)
+    assert np.array_equal(pop, summ[:, 0])                                        # mask popcount == changed pixels
+    for s in range(ns):
+        assert np.array_equal(ctx.get_prev_luma(s), prev[s])
+    ctx.close()
+
+
+def test_config2_1080p_batch64(lv, orc, torch_cuda):
+    _full_size(lv, orc, torch_cuda, 1920, 1080, 1, 64)
+
+
+def test_config3_4k_batch32(lv, orc, torch_cuda):
+    _full_size(lv, orc, torch_cuda, 3840, 2160, 1, 32)
+
+
+def test_config4_one_gpu_share_of_256_720p_streams(lv, orc, torch_cuda):
+    # the 8-GPU share of config 4: 32 streams x 16 frames of 720p in one launch
+    _full_size(lv, orc, torch_cuda, 1280, 720, 32, 16)
+
+
+def test_virtual_ranks_on_one_gpu_equal_single_rank(lv, orc, torch_cuda):
+    """Stream sharding is embarrassingly parallel: G virtual ranks (one context each, same GPU) produce, block by
+    block, exactly the single-rank result ('Multi-GPU without a cluster')."""
+    torch = torch_cuda
+    from livevideo_b200.shard import ShardedContext, shard_range
+    w, h, S, T = 352, 288, 7, 4
+    whole = ShardedContext(w, h, S, rank=0, world=1, device=0)
+    d_in = lv.gen_synthetic("camera", 3, 0, 0, S, T, w, h)
+    out = whole.ctx.alloc_outputs(S * T)
+    full = whole.step(d_in, T, out).cpu().numpy()
+    cnt_full = out["mb_count"].cpu().numpy().reshape(S, T, -1)
+    for G in (2, 3):
+        parts = []
+        for r in range(G):
+            first, count = shard_range(S, G, r)
+            sc = ShardedContext(w, h, S, rank=r, world=G, device=0)
+            fb = sc.ctx.frame_bytes
+            o = sc.ctx.alloc_outputs(max(count, 1) * T)
+            sc.step(d_in[first * T * fb:(first + count) * T * fb], T, o, gather=False)
+            torch.cuda.synchronize()
+            parts.append(o["summary"][:count * T * 2].cpu().numpy().reshape(count, T, 2))
+            assert np.array_equal(o["mb_count"][:count * T * sc.ctx.mbs].cpu().numpy().reshape(count, T, -1),
+                                  cnt_full[first:first + count])
+        assert np.array_equal(np.concatenate(parts), full)
