@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""bench.py -- Mpixel/s of the fused YUV420 -> BGR24 + frame-difference step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic frames: a single fused launch
+(lv_convert_diff_batch through the C ABI) over this rank's streams, plus -- at N > 1 -- the all-gather of the
+tiny per-(stream, frame) change summaries (the only exchange the path has).  Streams are sharded by stream ID,
+one process per GPU, no pixel ever crosses GPUs; per-GPU work is fixed as N grows ("weak").
+
+Printed JSON line (rank 0): value = whole-job Mpx/s with inputs resident in HBM; e2e = the same metric through
+lv_step_host with pinned HOST buffers (H2D of the frames and D2H of every output inside the timed region);
+roofline = algorithmic bytes (5.5 B/px) / mean kernel time vs the measured HBM copy bandwidth; cpu_baseline =
+the CPU oracle port (all host threads) on a bounded sample of the same workload, timed in the same run.
+`--impl reference` times that CPU path alone (the reference has no other implementation of this path).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_PX = 5.5          # 1.5 in (Y+U+V) + 3 out (BGR) + 1 previous luma   
+WORKLOADS = {
+    # name: (width, height, streams per GPU, frames per step)      BASELINE.json configs[1..3]
+    "1080p_x64": (1920, 1080, 1, 64),
+    "4k_x32": (3840, 2160, 1, 32),
+    "720p_32streams_x16": (1280, 720, 32, 16),      # one GPU's share of the 256-stream config at 8 GPUs
+    "cif_x300": (352, 288, 1, 300),
+}
+DEFAULT_WORKLOAD = "1080p_x64"
+METRIC = "Mpixel/s fused YUV420->BGR24 + frame-diff"
+
+
+def config_of(workload, world):
+    w, h, ns, nf = WORKLOADS[workload]
+    return {"workload": workload, "width": w, "height": h, "streams_per_gpu": ns, "frames_per_step": nf,
+            "streams_total": ns * world, "generator": "camera (seed 1)", "tol": 20, "mb_thresh": 0,
+            "outputs": "bgr + mb_count + mb_map + summary (bit mask off)"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=0, help="host-buffer steps to time (default: min(steps, 20))")
+    ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall-clock budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload, {}).get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        return None
+
+
+# ---- clocks during the timed region (NVML; same fields as the nvidia-smi recipe line) -----------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.ok = False
+
+    def sample(self):
+        if not self.ok:
+            return
+        try:
+            self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            try:
+                r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:  # noqa: BLE001
+                r = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self.sample()
+            self._stop.wait(0.005)
+
+    def start(self):
+        if self.ok:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---- CPU legs (the only place bench.py executes oracle/) ------------------------------------------------------
+def cpu_leg(w, h, ns, nf, budget_s, threads, min_reps=1, max_reps=50):
+    """Times the CPU oracle port of the path (oracle/lv_oracle.c, multi-threaded, one frame per task)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import lvoracle as orc
+    # bounded sample: at most 64 frames of the workload's geometry
+    s_ns = min(ns, 4)
+    s_nf = min(nf, max(1, 64 // s_ns))
+    frames = orc.gen_batch("camera", 1, s_ns, s_nf, w, h)
+    prev = np.zeros((s_ns, w * h), dtype=np.uint8)
+    px = s_ns * s_nf * w * h
+    orc.convert_diff_batch(frames, prev, s_ns, s_nf, w, h, 20, 0, want_mask=False, n_threads=threads)   # warm-up
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < min_reps or (time.perf_counter() < t_end and len(times) < max_reps):
+        prev[:] = 0
+        t0 = time.perf_counter()
+        orc.convert_diff_batch(frames, prev, s_ns, s_nf, w, h, 20, 0, want_mask=False, n_threads=threads)
+        times.append(time.perf_counter() - t0)
+    best, med = min(times), sorted(times)[len(times) // 2]
+    return {"mpx_s_median": px / med / 1e6, "mpx_s_best": px / best / 1e6, "reps": len(times), "px": px,
+            "sample": f"{s_ns} stream(s) x {s_nf} frames of {w}x{h} ('camera' generator), {len(times)} repetitions",
+            "times": times}
+
+
+def oracle32_leg(w, h):
+    """Single-thread timing of the reference's ORIGINAL object code (conversion only), when it can execute."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import lvoracle as orc
+        if not orc.have_oracle32():
+            return None
+        fr = orc.gen("uniform", 1, 0, 0, w, h)
+        reps = max(1, int(2e8 / (w * h)))
+        sec, _ = orc.oracle32_time(fr, w, h, reps)
+        return {"mpx_s": reps * w * h / sec / 1e6, "threads": 1, "what": "cscc.lib YV12_to_RGB24 only (no difference)"}
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w, h, ns, nf = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import lvoracle as orc
+    s_ns, s_nf = min(ns, 4), min(nf, max(1, 64 // min(ns, 4)))
+    frames = orc.gen_batch("camera", 1, s_ns, s_nf, w, h)
+    prev = np.zeros((s_ns, w * h), dtype=np.uint8)
+    px = s_ns * s_nf * w * h
+    for _ in range(max(args.warmup, 1) if args.warmup < 4 else 3):
+        orc.convert_diff_batch(frames, prev, s_ns, s_nf, w, h, 20, 0, want_mask=False, n_threads=threads)
+    steps = max(1, min(args.steps, 200))
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        orc.convert_diff_batch(frames, prev, s_ns, s_nf, w, h, 20, 0, want_mask=False, n_threads=threads)
+        done += 1
+        if time.perf_counter() - t0 > 120:
+            break
+    dt = time.perf_counter() - t0
+    val = px * done / dt / 1e6
+    sample = f"each step = {s_ns} stream(s) x {s_nf} frames of {w}x{h}; {done} steps timed"
+    cfg = config_of(args.workload, max(args.gpus, 1))
+    cfg["reference_arm"] = ("CPU port of the reference path (oracle/lv_oracle.c: cscc.lib tables + IsNearlyZero loops), "
+                            f"{threads} host threads, one frame per task")
+    line = {"impl": "reference", "metric": METRIC,
+            "value": val, "unit": "Mpx/s", "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
+            "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": val, "unit": "Mpx/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---- the GPU arm ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import livevideo_b200 as lv
+    from livevideo_b200.shard import ShardedContext
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- livevideo_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w, h, ns, nf = WORKLOADS[args.workload]
+    total_streams = ns * world
+    sc = ShardedContext(w, h, total_streams, 20, 0, rank=rank, world=world, device=local_rank)
+    ctx = sc.ctx
+    n = ns * nf
+    px_step = n * w * h
+    d_in = lv.gen_synthetic("camera", 1, sc.first_stream, 0, ns, nf, w, h, device=local_rank)
+    out = ctx.alloc_outputs(n)
+    working_set = n * (ctx.frame_bytes + ctx.bgr_bytes)
+
+    def step():
+        return sc.step(d_in, nf, out, gather=world > 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    launches0 = ctx.kernel_launches
+    sampler.start()
+    for i in range(args.steps):
+        ev[2 * i].record()
+        ctx.convert_diff_batch(d_in, ns, nf, out)
+        ev[2 * i + 1].record()
+        if world > 1:
+            from livevideo_b200.shard import gather_summaries
+            gather_summaries(out["summary"][: n * 2], total_streams, nf)
+    sampler.sample()
+    barrier()
+    sampler.stop()
+    launches = ctx.kernel_launches - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kern_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
+    if world > 1:
+        t = torch.tensor([total_ms, kern_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kern_ms = float(t[0]), float(t[1])
+    value = px_step * world * args.steps / (total_ms * 1e-3) / 1e6
+
+    # end to end: pinned host buffers in, every output back in host memory
+    e2e = None
+    if not args.no_e2e:
+        e_steps = args.e2e_steps or max(3, min(args.steps, 20))
+        h_in = lv.pinned(n * ctx.frame_bytes)
+        h_in.array[:] = d_in.cpu().numpy()
+        h_bgr = lv.pinned(n * ctx.bgr_bytes)
+        h_cnt = lv.pinned(2 * n * ctx.mbs, np.uint16)
+        h_map = lv.pinned(n * ctx.mbs)
+        h_sum = lv.pinned(8 * n, np.uint32)
+
+        def host_step():
+            ctx.step_host(h_in.array, ns, nf, bgr=h_bgr.array, mb_count=h_cnt.array, mb_map=h_map.array,
+                          summary=h_sum.array)
+        for _ in range(3):
+            host_step()
+        barrier()
+        l0 = ctx.kernel_launches
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            host_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        e2e_launches = ctx.kernel_launches - l0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        h2d = n * ctx.frame_bytes
+        d2h = n * (ctx.bgr_bytes + 3 * ctx.mbs + 8)
+        e2e = {"value": px_step * world * e_steps / dt / 1e6, "unit": "Mpx/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": dt / e_steps * 1e3,
+               "gpu_launches": e2e_launches, "api": "lv_step_host (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)",
+               "pcie_gbs": (h2d + d2h) * e_steps / dt / 1e9}
+        # sanity: the host path returned the same summaries as the device path
+        if not np.array_equal(h_sum.array.view(np.uint32), out["summary"].cpu().numpy().view(np.uint32)):
+            # the device path was stepped many times on the same batch: frame 0 differs once the state has
+            # carried the last frame; compare frames t >= 1 only
+            a = h_sum.array.view(np.uint32).reshape(ns, nf, 2)[:, 1:]
+            b = out["summary"].cpu().numpy().view(np.uint32).reshape(ns, nf, 2)[:, 1:]
+            assert np.array_equal(a, b), "host step and device step disagree"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    achieved = px_step * BYTES_PER_PX / (kern_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": dict(config_of(args.workload, world),
+                       l2=f"no flush: the step streams {working_set / 1e6:.0f} MB per GPU (> 126 MB L2) between "
+                          "two uses of any byte"),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
+                     "algorithmic_bytes_per_px": BYTES_PER_PX, "px_per_launch": px_step,
+                     "kernel_us": kern_ms * 1e3, "frac_of_nominal_8TBs": achieved / 8000.0},
+        "clocks": sampler.summary(),
+        "gpu_launches": int(launches),
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        c = cpu_leg(w, h, ns, nf, args.cpu_seconds, threads)
+        c1 = cpu_leg(w, h, 1, min(nf, 8), min(args.cpu_seconds, 2.0), 1)
+        line["cpu_baseline"] = {"value": c["mpx_s_median"], "unit": "Mpx/s", "cores": threads, "kind": "port",
+                                "sample": c["sample"], "best": c["mpx_s_best"],
+                                "single_thread_mpx_s": c1["mpx_s_median"],
+                                "reference_object_code_single_thread": oracle32_leg(w, h)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

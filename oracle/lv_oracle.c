@@ -26,9 +26,22 @@ static inline int32_t sar(int32_t v, int s)
     return v >= 0 ? (v >> s) : -(int32_t)(((uint32_t)(-(v + 1)) >> s) + 1);
 }
 
+/* The hot loops use the compiler's signed >> directly; lvo_init_tables() verifies once that it is the
+ * arithmetic (floor) shift of the original's `sar`, as gcc/clang guarantee on x86-64. */
+#define SAR15(v) ((int32_t)(v) >> 15)
+#if defined(__GNUC__) && defined(__x86_64__) && !defined(LVO_NO_CLONES)
+#define LVO_HOT __attribute__((target_clones("avx2", "default")))
+#else
+#define LVO_HOT
+#endif
+
 void lvo_init_tables(void)
 {
     if (tables_ready) return;
+    {
+        volatile int32_t m1 = -1, m3 = -98305;
+        if ((m1 >> 1) != -1 || (m3 >> 15) != -4) abort();   /* signed >> must be arithmetic */
+    }
     for (int i = 0; i < 256; i++) {
         crv_tab[i] = sar(104597 * (i - 128), 15);
         cbu_tab[i] = sar(132201 * (i - 128), 15);
@@ -74,8 +87,8 @@ void lvo_textbook_px(int y, int u, int v, uint8_t bgr[3])
  * Loop counts are (w+3)>>2 and (h+1)>>1, so the original needs w%4==0 and h%2==0 to stay in
  * bounds; the restatement keeps the same traversal and therefore the same precondition.
  */
-void lvo_yv12_to_rgb24(const uint8_t *src_y, const uint8_t *src_u, const uint8_t *src_v,
-                       uint8_t *dst, int width, int height)
+LVO_HOT void lvo_yv12_to_rgb24(const uint8_t *src_y, const uint8_t *src_u, const uint8_t *src_v,
+                               uint8_t *dst, int width, int height)
 {
     lvo_init_tables();
     const uint8_t *py1 = src_y, *py2 = src_y + width;
@@ -89,7 +102,7 @@ void lvo_yv12_to_rgb24(const uint8_t *src_y, const uint8_t *src_u, const uint8_t
                 int u = src_u[k], v = src_v[k];
                 cb[k] = cbu_tab[u];
                 cr[k] = crv_tab[v];
-                cg[k] = sar(cgu_tab[u] + cgv_tab[v], 15);   /* add, then ONE sar: +0x412, +0x45c */
+                cg[k] = SAR15(cgu_tab[u] + cgv_tab[v]);     /* add, then ONE sar: +0x412, +0x45c */
             }
             for (int p = 0; p < 4; p++) {
                 int k = p >> 1;
@@ -115,29 +128,49 @@ int lvo_is_nearly_zero(int a, int tol)
     return ((a >= 0) && (a <= tol)) || ((a < 0) && (a >= -tol));
 }
 
-uint32_t lvo_frame_diff_mb(const uint8_t *cur_y, const uint8_t *ref_y, int width, int height,
-                           int tol, int mb_thresh, uint8_t *mask, uint16_t *mb_count, uint8_t *mb_map)
+/* !IsNearlyZero(a, tol) with the macro body of image.h:22 written out, branch-free so the row loop vectorises */
+static inline int changed_px(int a, int tol)
+{
+    return !((((a) >= 0) & ((a) <= (tol))) | (((a) < 0) & ((a) >= -(tol))));
+}
+
+LVO_HOT uint32_t lvo_frame_diff_mb(const uint8_t *cur_y, const uint8_t *ref_y, int width, int height,
+                                   int tol, int mb_thresh, uint8_t *mask, uint16_t *mb_count, uint8_t *mb_map)
 {
     const int mb_w = (width + 15) / 16, mb_h = (height + 15) / 16;
     uint32_t total = 0;
-    /* image.c:4978-4981: for mby, for mbx: k = mby*mbwidth + mbx; 5143-5150: scan the 16x16 block */
-    for (int mby = 0; mby < mb_h; mby++)
-        for (int mbx = 0; mbx < mb_w; mbx++) {
-            int k = mby * mb_w + mbx;
-            int start_px = mbx * 16, start_py = mby * 16;
-            uint32_t cnt = 0;
-            for (int py = start_py; py < start_py + 16 && py < height; py++)
-                for (int px = start_px; px < start_px + 16 && px < width; px++) {
-                    /* image.c:4795-4803 / MainDlg.cpp:806: uchar operands promote to int */
-                    int a = (int)cur_y[py * width + px] - (int)ref_y[py * width + px];
-                    int m = lvo_is_nearly_zero(a, tol) ? 0 : 1;
-                    if (mask) mask[py * width + px] = (uint8_t)m;
-                    cnt += (uint32_t)m;
+    /* Same result as scanning each 16x16 block (image.c:4978-4981, 5143-5150: k = mby*mbwidth + mbx,
+     * py in [16*mby, 16*mby+16), px in [16*mbx, 16*mbx+16)), traversed row by row so every pixel is
+     * touched once in memory order; per pixel image.c:4795-4803 / MainDlg.cpp:806 (uchar promotes to int). */
+    uint32_t *acc = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)mb_w);
+    for (int mby = 0; mby < mb_h; mby++) {
+        memset(acc, 0, sizeof(uint32_t) * (size_t)mb_w);
+        for (int py = mby * 16; py < mby * 16 + 16 && py < height; py++) {
+            const uint8_t *c = cur_y + (size_t)py * width, *r = ref_y + (size_t)py * width;
+            uint8_t *mrow = mask ? mask + (size_t)py * width : NULL;
+            for (int mbx = 0; mbx < mb_w; mbx++) {
+                const int x0 = mbx * 16, x1 = x0 + 16 < width ? x0 + 16 : width;
+                uint32_t cnt = 0;
+                if (mrow) {
+                    for (int px = x0; px < x1; px++) {
+                        int m = changed_px((int)c[px] - (int)r[px], tol);
+                        mrow[px] = (uint8_t)m;
+                        cnt += (uint32_t)m;
+                    }
+                } else {
+                    for (int px = x0; px < x1; px++) cnt += (uint32_t)changed_px((int)c[px] - (int)r[px], tol);
                 }
-            if (mb_count) mb_count[k] = (uint16_t)cnt;
-            if (mb_map) mb_map[k] = (uint8_t)((int)cnt > mb_thresh);
-            total += cnt;
+                acc[mbx] += cnt;
+            }
         }
+        for (int mbx = 0; mbx < mb_w; mbx++) {
+            const int k = mby * mb_w + mbx;
+            if (mb_count) mb_count[k] = (uint16_t)acc[mbx];
+            if (mb_map) mb_map[k] = (uint8_t)((int)acc[mbx] > mb_thresh);
+            total += acc[mbx];
+        }
+    }
+    free(acc);
     return total;
 }
 
