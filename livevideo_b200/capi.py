@@ -52,7 +52,7 @@ class LiveVideoError(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB_PATH
+    return os.environ.get("LV_LIB_OVERRIDE", _build.LIB_PATH)   # development only: A/B builds of the same ABI
 
 
 def lib():

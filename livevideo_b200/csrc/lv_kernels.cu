@@ -15,6 +15,12 @@
 #include "lv_kernels.h"
 #include "lv_pixel.cuh"
 
+#include <cstdlib>
+
+#ifndef LV_DEFAULT_TMA
+#define LV_DEFAULT_TMA 0
+#endif
+
 namespace lv {
 
 namespace {
@@ -188,8 +194,8 @@ __global__ void k_convert_generic(int w, int h, const uint8_t *__restrict__ y, c
         const uint32_t t2 = luma_pair(yp[0], yp[1]);
         const uint32_t B = chan_pair(t2, c.cb2), G = chan_pair(t2, c.ng2), R = chan_pair(t2, c.cr2);
         uint8_t *d = bgr + (size_t)(h - 1 - row) * 3 * w + 6 * cx;
-        d[0] = (uint8_t)B; d[1] = (uint8_t)G; d[2] = (uint8_t)R;
-        d[3] = (uint8_t)(B >> 16); d[4] = (uint8_t)(G >> 16); d[5] = (uint8_t)(R >> 16);
+        d[0] = (uint8_t)(B >> 8); d[1] = (uint8_t)(G >> 8); d[2] = (uint8_t)(R >> 8);
+        d[3] = (uint8_t)(B >> 24); d[4] = (uint8_t)(G >> 24); d[5] = (uint8_t)(R >> 24);
     }
 }
 
@@ -214,8 +220,21 @@ __global__ void k_diff_generic(int w, int h, const uint8_t *__restrict__ cur, co
 
 }  // namespace
 
+// Kernel selection (development switch): LV_KERNEL=tma | tile.  Both produce identical bytes.
+static bool use_tma()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LV_KERNEL");
+        v = e ? (e[0] == 't' && e[1] == 'm') : LV_DEFAULT_TMA;
+    }
+    return v != 0;
+}
+
 int launch_step(const StepArgs &s, cudaStream_t st)
 {
+    if (use_tma())
+        if (int r = launch_step_tma(s, st)) return r;   // 0 = geometry/alignment not eligible for the TMA pipeline
     KArgs a{};
     a.g = s.g; a.y0 = s.i420; a.y_stride = s.g.frame; a.ref_planes = nullptr;
     a.state_in = s.state_in; a.state_out = s.state_out; a.n_frames = s.n_frames;
@@ -228,6 +247,8 @@ int launch_step(const StepArgs &s, cudaStream_t st)
 
 int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st)
 {
+    if (use_tma())
+        if (int r = launch_convert_tma(g, i420, n_frames, bgr, st)) return r;
     KArgs a{};
     a.g = g; a.y0 = i420; a.y_stride = g.frame; a.n_frames = n_frames > 0 ? n_frames : 1; a.bgr = bgr;
     return launch_tile<true, false>(a, n_frames, st);
@@ -235,6 +256,8 @@ int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bg
 
 int launch_diff(const DiffArgs &d, cudaStream_t st)
 {
+    if (use_tma())
+        if (int r = launch_diff_tma(d, st)) return r;
     KArgs a{};
     a.g = d.g; a.y0 = d.cur_y; a.y_stride = d.g.px; a.ref_planes = d.ref_y; a.n_frames = 1;
     a.tol = d.tol; a.mb_thresh = d.mb_thresh;

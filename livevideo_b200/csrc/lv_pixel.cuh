@@ -26,11 +26,17 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     return __byte_perm(a, b, sel);
 }
 
-// byte k (0..3) of w, zero extended
+// byte k (0..3) of w, zero extended.  IDP.4A with a one-hot byte selector: the dot-product unit sits on
+// the FMA pipe, so the 48 byte extractions per 32 pixels stay off the ALU pipe (PRMT/LOP3/SHF/VIADDMNMX)
+// that bounds this kernel (measured: tools/ubench/pipes.cu).
 template <int K>
 __device__ __forceinline__ int ubyte(uint32_t w)
 {
+#ifdef LV_UBYTE_PRMT
     return (int)prmt(w, 0u, 0x4440u | (uint32_t)K);
+#else
+    return (int)__dp4a(w, 1u << (8 * K), 0u);
+#endif
 }
 
 // Chroma terms of one (U,V) sample, each duplicated into both halfwords (the two pixels of a
@@ -60,11 +66,13 @@ __device__ __forceinline__ uint32_t luma_pair(int ya, int yb)
     return prmt((uint32_t)TA, (uint32_t)TB, 0x7632u);
 }
 
-// add + clamp to [0,511] per halfword, then >>1: low byte of each halfword is the channel value
-// (bit 15 of the low halfword may carry garbage from the upper one; it is never selected).
+// add + clamp to [0,511] per halfword (one VIADDMNMX), then *128: the channel value x>>1 lands in the
+// HIGH byte of each halfword (bytes 1 and 3); the low bytes hold only the discarded bit and are never
+// selected.  The multiply is an IMAD, i.e. it runs on the FMA pipe instead of the ALU pipe (SHF) that
+// bounds this kernel.
 __device__ __forceinline__ uint32_t chan_pair(uint32_t t2, uint32_t c2)
 {
-    return __viaddmin_s16x2_relu(t2, c2, 0x01ff01ffu) >> 1;
+    return __viaddmin_s16x2_relu(t2, c2, 0x01ff01ffu) * 128u;
 }
 
 // 4 pixels (one 32-bit word of luma, two chroma samples) -> 12 bytes B,G,R,B,G,R,...
@@ -75,10 +83,10 @@ __device__ __forceinline__ void convert4(uint32_t yw, const Chroma2 &c0, const C
     const uint32_t tb = luma_pair(ubyte<2>(yw), ubyte<3>(yw));
     const uint32_t Ba = chan_pair(ta, c0.cb2), Ga = chan_pair(ta, c0.ng2), Ra = chan_pair(ta, c0.cr2);
     const uint32_t Bb = chan_pair(tb, c1.cb2), Gb = chan_pair(tb, c1.ng2), Rb = chan_pair(tb, c1.cr2);
-    // pixel p of pair x sits in byte 0 (even) / byte 2 (odd) of Bx,Gx,Rx
-    o0 = prmt(prmt(Ba, Ga, 0x2040u), Ra, 0x3410u);                       // b0 g0 r0 b1
-    o1 = prmt(prmt(prmt(Ga, Ra, 0x0062u), Bb, 0x0410u), Gb, 0x4210u);    // g1 r1 b2 g2
-    o2 = prmt(prmt(Rb, Bb, 0x2060u), Gb, 0x3610u);                       // r2 b3 g3 r3
+    // pixel p of pair x sits in byte 1 (even) / byte 3 (odd) of Bx,Gx,Rx
+    o0 = prmt(prmt(Ba, Ga, 0x3051u), Ra, 0x3510u);                       // b0 g0 r0 b1
+    o1 = prmt(prmt(prmt(Ga, Ra, 0x0073u), Bb, 0x0510u), Gb, 0x5210u);    // g1 r1 b2 g2
+    o2 = prmt(prmt(Rb, Bb, 0x3071u), Gb, 0x3710u);                       // r2 b3 g3 r3
 }
 
 // per-byte (|a-b| > tol) for 4 pixels: returns a word whose bit 7 of byte k is the result for
@@ -104,6 +112,18 @@ __device__ __forceinline__ uint32_t diff_mask16(const uint4 &cur, const uint4 &r
     const uint32_t g2 = (diff_gt4(cur.z, ref.z, tol4, ntol7) & 0x80808080u) * 0x00204081u >> 28;
     const uint32_t g3 = (diff_gt4(cur.w, ref.w, tol4, ntol7) & 0x80808080u) * 0x00204081u >> 28;
     return g0 | (g1 << 4) | (g2 << 8) | (g3 << 12);
+}
+
+// 16 pixels -> acc + 128 * (number of changed pixels): bit 7 of each byte summed by one IDP.4A per word
+// (the dot product runs on the FMA pipe, off the ALU pipe that bounds this kernel)
+__device__ __forceinline__ uint32_t diff_count16(const uint4 &cur, const uint4 &ref, uint32_t tol4, uint32_t ntol7,
+                                                 uint32_t acc)
+{
+    acc = __dp4a(diff_gt4(cur.x, ref.x, tol4, ntol7) & 0x80808080u, 0x01010101u, acc);
+    acc = __dp4a(diff_gt4(cur.y, ref.y, tol4, ntol7) & 0x80808080u, 0x01010101u, acc);
+    acc = __dp4a(diff_gt4(cur.z, ref.z, tol4, ntol7) & 0x80808080u, 0x01010101u, acc);
+    acc = __dp4a(diff_gt4(cur.w, ref.w, tol4, ntol7) & 0x80808080u, 0x01010101u, acc);
+    return acc;
 }
 
 // expand 4 mask bits (bits 4k..4k+3 of m) to 4 bytes of 0/1

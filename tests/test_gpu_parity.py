@@ -159,7 +159,8 @@ def test_fused_threshold_sweep(lv, orc, torch_cuda, tol, thr):
 
 def test_fused_ragged_widths_and_tiny_frames(lv, orc, torch_cuda):
     # widths that do not fill a 512-pixel block tile, heights with 1..8 row pairs in the last MB row
-    for (w, h) in [(16, 2), (16, 16), (48, 18), (528, 20), (1040, 30), (4112, 2)]:
+    for (w, h) in [(16, 2), (16, 16), (48, 18), (528, 20), (1040, 30), (4112, 2), (64, 18), (96, 20), (160, 8), (32, 2),
+                   (352, 30), (4096, 24)]:
         frames = orc.gen_batch("camera" if h >= 16 and w >= 16 and h // 8 > 0 and w // 8 > 0 and w > w // 8 else "uniform",
                                3, 2, 2, w, h) if h >= 16 else orc.gen_batch("uniform", 3, 2, 2, w, h)
         prev = np.zeros((2, w * h), np.uint8)
