@@ -136,6 +136,12 @@ LV_API int lv_step_host(lv_ctx *ctx, const uint8_t *h_i420, int first_stream, in
 LV_API int lv_gen_synthetic(int kind, uint32_t seed, uint32_t first_stream, uint32_t first_frame, int n_streams,
                             int n_frames, int width, int height, uint8_t *d_i420, void *cuda_stream);
 
+/* ---- kernel variant (process-wide) -------------------------------------------------------------------
+ * 0 = tiled kernel (default), 1 = TMA pipeline (cp.async.bulk.tensor loads/stores), 2 = register-pipelined
+ * strips.  All variants are bit-identical; the choice only affects speed (DESIGN.md has the measurements). */
+LV_API int lv_set_kernel_variant(int variant);
+LV_API int lv_get_kernel_variant(void);
+
 /* ---- introspection for the benchmark ------------------------------------------------------------- */
 LV_API uint64_t lv_kernel_launches(const lv_ctx *ctx);   /* kernels of this library launched so far */
 LV_API int lv_device_sm_count(const lv_ctx *ctx);

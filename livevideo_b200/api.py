@@ -247,6 +247,19 @@ def pinned(nbytes, dtype=np.uint8):
     return PinnedArray(nbytes, dtype)
 
 
+KERNEL_VARIANTS = {"tile": 0, "tma": 1, "strip": 2}
+
+
+def set_kernel_variant(name):
+    """Select the kernel variant ("tile" default, "tma", "strip"); all are bit-identical."""
+    capi.check(capi.lib().lv_set_kernel_variant(KERNEL_VARIANTS[name]), "lv_set_kernel_variant")
+
+
+def get_kernel_variant():
+    v = capi.lib().lv_get_kernel_variant()
+    return {n: k for k, n in KERNEL_VARIANTS.items()}[v]
+
+
 def gen_synthetic(kind, seed, first_stream, first_frame, n_streams, n_frames, width, height, out=None, device=0,
                   cuda_stream=None):
     """Synthetic I420 frames on the device (`uniform` or `camera` generator)."""

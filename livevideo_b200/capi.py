@@ -34,6 +34,8 @@ SYMBOLS = {
     "lv_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "lv_host_free": (C.c_int, [_vp]),
     "lv_step_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lv_set_kernel_variant": (C.c_int, [C.c_int]),
+    "lv_get_kernel_variant": (C.c_int, []),
     "lv_kernel_launches": (C.c_uint64, [_vp]),
     "lv_device_sm_count": (C.c_int, [_vp]),
     "lv_gen_synthetic": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int,

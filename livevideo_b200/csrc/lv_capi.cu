@@ -306,6 +306,15 @@ int lv_diff_batch(lv_ctx *c, const uint8_t *d_cur_y, const uint8_t *d_ref_y, int
     return launch_result(lv::launch_diff(a, st), c->launches);
 }
 
+int lv_set_kernel_variant(int variant)
+{
+    if (variant < 0 || variant > 2) return LV_E_ARG;
+    lv::set_kernel_variant(variant);
+    return LV_OK;
+}
+
+int lv_get_kernel_variant(void) { return lv::kernel_variant(); }
+
 int lv_host_alloc(void **p, size_t bytes)
 {
     if (!p) return LV_E_ARG;

@@ -17,6 +17,9 @@
 
 #include <cstdlib>
 
+#ifndef LV_TILE_MINBLOCKS
+#define LV_TILE_MINBLOCKS 5
+#endif
 #ifndef LV_DEFAULT_TMA
 #define LV_DEFAULT_TMA 0
 #endif
@@ -32,7 +35,8 @@ struct KArgs {
     const uint8_t *ref_planes;  // K3: explicit reference planes (stride px); else NULL
     const uint8_t *state_in;    // K1: carried previous luma, one plane per stream
     uint8_t *state_out;
-    int n_frames;               // frames per stream (t = f % n_frames)
+    int n_frames;               // frames per stream
+    uint32_t nf_magic;          // ceil(2^32 / n_frames): f / n_frames == umulhi(f, magic) for f < 2^16
     int f_base;                 // first frame index of this launch (gridDim.z is limited to 65535)
     int tol, mb_thresh;
     uint8_t *bgr;
@@ -61,8 +65,11 @@ __device__ __forceinline__ void convert_row16(const uint4 &y, const Chroma2 (&c)
     st16_stream(dst + 32, o2);
 }
 
-template <bool kConv, bool kDiff>
-__global__ void __launch_bounds__(256) k_tile(const KArgs a)
+// All addressing is a block-uniform 64-bit base (frame / plane starts) plus one 32-bit per-thread offset;
+// the frame -> (stream, t) split is a multiply-high by a host-computed reciprocal.  The optional mask
+// outputs live in their own instantiation (kMask) so the common path carries none of their code.
+template <bool kConv, bool kDiff, bool kMask>
+__global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
 {
     const Geom &g = a.g;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -70,48 +77,53 @@ __global__ void __launch_bounds__(256) k_tile(const KArgs a)
     const int row0 = blockIdx.y * 16 + 2 * ty;
     const int f = a.f_base + blockIdx.z;
     const bool active = unit < g.units && row0 < g.h;
+    const int w = g.w;
 
     uint32_t cnt = 0;
     if (active) {
         const uint8_t *yf = a.y0 + (size_t)f * a.y_stride;
-        const size_t off = (size_t)row0 * g.w + (size_t)unit * 16;
-        const uint4 y0 = ld16(yf + off);
-        const uint4 y1 = ld16(yf + off + g.w);
+        const uint32_t off = (uint32_t)row0 * (uint32_t)w + (uint32_t)unit * 16u;
+        const uint4 y0 = ld16(yf + off);          // re-read by the next frame as its reference: keep in L2
+        const uint4 y1 = ld16(yf + off + w);
 
         if constexpr (kDiff) {
-            const int t = f % a.n_frames;
+            const int s = a.n_frames == 1 ? f : (int)__umulhi((uint32_t)f, a.nf_magic);
+            const int t = f - s * a.n_frames;
             const uint8_t *ref;
             if (a.ref_planes) ref = a.ref_planes + (size_t)f * g.px;
-            else if (t == 0) ref = a.state_in + (size_t)(f / a.n_frames) * g.px;
-            else ref = yf - a.y_stride;
+            else ref = (t == 0) ? a.state_in + (size_t)s * g.px : yf - a.y_stride;
             const uint4 p0 = ld16_stream(ref + off);
-            const uint4 p1 = ld16_stream(ref + off + g.w);
+            const uint4 p1 = ld16_stream(ref + off + w);
             const uint32_t tol4 = (uint32_t)a.tol * 0x01010101u;
             const uint32_t ntol7 = ~tol4 & 0x7f7f7f7fu;
-            const uint32_t m0 = diff_mask16(y0, p0, tol4, ntol7);
-            const uint32_t m1 = diff_mask16(y1, p1, tol4, ntol7);
-            cnt = __popc(m0) + __popc(m1);
-            if (a.mask_bits) {
-                uint16_t *mb = a.mask_bits + ((size_t)f * g.h + row0) * g.units + unit;
-                mb[0] = (uint16_t)m0;
-                mb[g.units] = (uint16_t)m1;
-            }
-            if (a.mask_bytes) {
-                uint8_t *mp = a.mask_bytes + (size_t)f * g.px + off;
-                st16_stream(mp, make_uint4(mask_bytes4(m0, 0), mask_bytes4(m0, 1), mask_bytes4(m0, 2), mask_bytes4(m0, 3)));
-                st16_stream(mp + g.w, make_uint4(mask_bytes4(m1, 0), mask_bytes4(m1, 1), mask_bytes4(m1, 2), mask_bytes4(m1, 3)));
+            if constexpr (kMask) {
+                const uint32_t m0 = diff_mask16(y0, p0, tol4, ntol7);
+                const uint32_t m1 = diff_mask16(y1, p1, tol4, ntol7);
+                cnt = (uint32_t)(__popc(m0) + __popc(m1)) << 7;
+                if (a.mask_bits) {
+                    uint16_t *mb = a.mask_bits + ((size_t)f * g.h + row0) * g.units + unit;
+                    mb[0] = (uint16_t)m0;
+                    mb[g.units] = (uint16_t)m1;
+                }
+                if (a.mask_bytes) {
+                    uint8_t *mp = a.mask_bytes + (size_t)f * g.px + off;
+                    st16_stream(mp, make_uint4(mask_bytes4(m0, 0), mask_bytes4(m0, 1), mask_bytes4(m0, 2), mask_bytes4(m0, 3)));
+                    st16_stream(mp + w, make_uint4(mask_bytes4(m1, 0), mask_bytes4(m1, 1), mask_bytes4(m1, 2), mask_bytes4(m1, 3)));
+                }
+            } else {
+                cnt = diff_count16(y1, p1, tol4, ntol7, diff_count16(y0, p0, tol4, ntol7, 0u));
             }
             if (a.state_out && t == a.n_frames - 1) {
                 // prev_frm <- curr_frm (lib/JM/image.c:1553-1561): the last frame becomes the state
-                uint8_t *so = a.state_out + (size_t)(f / a.n_frames) * g.px + off;
+                uint8_t *so = a.state_out + (size_t)s * g.px + off;
                 *reinterpret_cast<uint4 *>(so) = y0;
-                *reinterpret_cast<uint4 *>(so + g.w) = y1;
+                *reinterpret_cast<uint4 *>(so + w) = y1;
             }
         }
 
         if constexpr (kConv) {
             const uint8_t *uf = yf + g.px;
-            const size_t coff = (size_t)(row0 >> 1) * (g.w >> 1) + (size_t)unit * 8;
+            const uint32_t coff = (uint32_t)(row0 >> 1) * (uint32_t)(w >> 1) + (uint32_t)unit * 8u;
             const uint2 u = ld8_stream(uf + coff);
             const uint2 v = ld8_stream(uf + (g.px >> 2) + coff);
             Chroma2 c[8];
@@ -124,13 +136,14 @@ __global__ void __launch_bounds__(256) k_tile(const KArgs a)
             c[6] = chroma_terms(ubyte<2>(u.y), ubyte<2>(v.y));
             c[7] = chroma_terms(ubyte<3>(u.y), ubyte<3>(v.y));
             // bottom-up DIB: source row r lands in destination row h-1-r (Convert.obj .text+0x350..0x39f)
-            uint8_t *d0 = a.bgr + (size_t)f * 3 * g.px + (size_t)(g.h - 1 - row0) * 3 * g.w + (size_t)unit * 48;
+            uint8_t *d0 = a.bgr + (size_t)f * 3 * g.px + ((uint32_t)(g.h - 1 - row0) * 3u * (uint32_t)w + (uint32_t)unit * 48u);
             convert_row16(y0, c, d0);
-            convert_row16(y1, c, d0 - (size_t)3 * g.w);
+            convert_row16(y1, c, d0 - 3 * w);
         }
     }
 
     if constexpr (kDiff) {
+        // 8 row-pair partial counts per macroblock -> shared memory -> the first warp finishes the block
         __shared__ uint32_t part[8][32];
         part[ty][tx] = cnt;
         __syncthreads();
@@ -138,6 +151,7 @@ __global__ void __launch_bounds__(256) k_tile(const KArgs a)
             uint32_t tot = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++) tot += part[i][tx];
+            tot >>= 7;                                     // diff_count16 counts in units of 128
             const bool valid = unit < g.units;
             const uint32_t on = valid && (int)tot > a.mb_thresh;
             if (valid) {
@@ -161,22 +175,32 @@ __global__ void __launch_bounds__(256) k_tile(const KArgs a)
     }
 }
 
-template <bool kConv, bool kDiff>
-int launch_tile(const KArgs &a, int total_frames, cudaStream_t st)
+template <bool kConv, bool kDiff, bool kMask>
+int launch_tile_t(const KArgs &a, int total_frames, cudaStream_t st)
 {
-    if (total_frames <= 0) return 0;
     int launches = 0;
     for (int f0 = 0; f0 < total_frames; f0 += 65535) {   // gridDim.z <= 65535
         const int nf = total_frames - f0 < 65535 ? total_frames - f0 : 65535;
         KArgs b = a;
         b.f_base = f0;
         dim3 grid((a.g.units + 31) / 32, a.g.mb_h, nf), block(32, 8);
-        k_tile<kConv, kDiff><<<grid, block, 0, st>>>(b);
+        k_tile<kConv, kDiff, kMask><<<grid, block, 0, st>>>(b);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return -(int)e;
         launches++;
     }
     return launches;
+}
+
+template <bool kConv, bool kDiff>
+int launch_tile(KArgs a, int total_frames, cudaStream_t st)
+{
+    if (total_frames <= 0) return 0;
+    // the multiply-high division is exact for f < 2^16 and n_frames < 2^16; longer batches are cut by the caller
+    a.nf_magic = a.n_frames > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)a.n_frames - 1) / (uint64_t)a.n_frames) : 0u;
+    const bool mask = a.mask_bits || a.mask_bytes;
+    if (kDiff && mask) return launch_tile_t<kConv, kDiff, kDiff>(a, total_frames, st);
+    return launch_tile_t<kConv, kDiff, false>(a, total_frames, st);
 }
 
 // ---- generic geometry (width % 4 == 0, not a multiple of 16): one thread per 2x2 quad ------------
@@ -194,8 +218,8 @@ __global__ void k_convert_generic(int w, int h, const uint8_t *__restrict__ y, c
         const uint32_t t2 = luma_pair(yp[0], yp[1]);
         const uint32_t B = chan_pair(t2, c.cb2), G = chan_pair(t2, c.ng2), R = chan_pair(t2, c.cr2);
         uint8_t *d = bgr + (size_t)(h - 1 - row) * 3 * w + 6 * cx;
-        d[0] = (uint8_t)(B >> 8); d[1] = (uint8_t)(G >> 8); d[2] = (uint8_t)(R >> 8);
-        d[3] = (uint8_t)(B >> 24); d[4] = (uint8_t)(G >> 24); d[5] = (uint8_t)(R >> 24);
+        d[0] = chan_even(B); d[1] = chan_even(G); d[2] = chan_even(R);
+        d[3] = chan_odd(B); d[4] = chan_odd(G); d[5] = chan_odd(R);
     }
 }
 
@@ -220,19 +244,26 @@ __global__ void k_diff_generic(int w, int h, const uint8_t *__restrict__ cur, co
 
 }  // namespace
 
-// Kernel selection (development switch): LV_KERNEL=tma | tile.  Both produce identical bytes.
-static bool use_tma()
+// Kernel variant: 0 = tiled (default, fastest: profiles/), 1 = TMA pipeline, 2 = register-pipelined strips.
+// All three produce identical bytes (tests/test_gpu_parity.py runs the parity suite over each).  The
+// environment variable LV_KERNEL=tile|tma|strip sets the initial value; lv_set_kernel_variant() overrides it.
+static int g_variant = -1;
+int kernel_variant()
 {
-    static int v = -1;
-    if (v < 0) {
+    if (g_variant < 0) {
         const char *e = getenv("LV_KERNEL");
-        v = e ? (e[0] == 't' && e[1] == 'm') : LV_DEFAULT_TMA;
+        g_variant = !e ? 0 : (e[0] == 's' ? 2 : (e[0] == 't' && e[1] == 'm') ? 1 : 0);
     }
-    return v != 0;
+    return g_variant;
 }
+void set_kernel_variant(int v) { g_variant = v < 0 || v > 2 ? 0 : v; }
+static bool use_tma() { return kernel_variant() == 1; }
+static bool use_strip() { return kernel_variant() == 2; }
 
 int launch_step(const StepArgs &s, cudaStream_t st)
 {
+    if (use_strip())
+        if (int r = launch_step_strip(s, st)) return r;
     if (use_tma())
         if (int r = launch_step_tma(s, st)) return r;   // 0 = geometry/alignment not eligible for the TMA pipeline
     KArgs a{};
@@ -241,12 +272,35 @@ int launch_step(const StepArgs &s, cudaStream_t st)
     a.tol = s.tol; a.mb_thresh = s.mb_thresh;
     a.bgr = s.bgr; a.mask_bits = s.mask_bits; a.mask_bytes = s.mask_bytes;
     a.mb_count = s.mb_count; a.mb_map = s.mb_map; a.summary = s.summary;
-    const int total = s.n_streams * s.n_frames;
-    return s.bgr ? launch_tile<true, true>(a, total, st) : launch_tile<false, true>(a, total, st);
+    if (s.n_frames > 65535) return -(int)cudaErrorInvalidValue;
+    // the kernel's frame -> (stream, t) split is exact below 2^16 frames per launch group: cut by streams
+    const int group = 65535 / s.n_frames;
+    const size_t mbs = (size_t)s.g.mb_w * s.g.mb_h;
+    int launches = 0;
+    for (int s0 = 0; s0 < s.n_streams; s0 += group) {
+        const int ns = s.n_streams - s0 < group ? s.n_streams - s0 : group;
+        const size_t f0 = (size_t)s0 * s.n_frames;
+        KArgs b = a;
+        b.y0 = a.y0 + f0 * s.g.frame;
+        b.state_in = a.state_in + (size_t)s0 * s.g.px;
+        if (a.state_out) b.state_out = a.state_out + (size_t)s0 * s.g.px;
+        if (a.bgr) b.bgr = a.bgr + f0 * 3 * s.g.px;
+        if (a.mask_bits) b.mask_bits = a.mask_bits + f0 * s.g.h * s.g.units;
+        if (a.mask_bytes) b.mask_bytes = a.mask_bytes + f0 * s.g.px;
+        if (a.mb_count) b.mb_count = a.mb_count + f0 * mbs;
+        if (a.mb_map) b.mb_map = a.mb_map + f0 * mbs;
+        if (a.summary) b.summary = a.summary + 2 * f0;
+        const int r = s.bgr ? launch_tile<true, true>(b, ns * s.n_frames, st) : launch_tile<false, true>(b, ns * s.n_frames, st);
+        if (r < 0) return r;
+        launches += r;
+    }
+    return launches;
 }
 
 int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st)
 {
+    if (use_strip())
+        if (int r = launch_convert_strip(g, i420, n_frames, bgr, st)) return r;
     if (use_tma())
         if (int r = launch_convert_tma(g, i420, n_frames, bgr, st)) return r;
     KArgs a{};
@@ -256,6 +310,8 @@ int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bg
 
 int launch_diff(const DiffArgs &d, cudaStream_t st)
 {
+    if (use_strip())
+        if (int r = launch_diff_strip(d, st)) return r;
     if (use_tma())
         if (int r = launch_diff_tma(d, st)) return r;
     KArgs a{};

@@ -58,12 +58,21 @@ int launch_step(const StepArgs &a, cudaStream_t st);
 int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st);
 int launch_diff(const DiffArgs &a, cudaStream_t st);
 
+int kernel_variant();
+void set_kernel_variant(int v);
+
 // The TMA pipeline (lv_tma.cu).  Return 0 when the geometry or a pointer alignment is not eligible
 // (the caller then uses the tiled kernel), >0 = kernels launched, <0 = -(cudaError_t).
 bool tma_supported(const Geom &g);
 int launch_step_tma(const StepArgs &a, cudaStream_t st);
 int launch_convert_tma(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st);
 int launch_diff_tma(const DiffArgs &a, cudaStream_t st);
+
+// The register-pipelined strip kernel (lv_strip.cu); same return convention.
+bool strip_supported(const Geom &g);
+int launch_step_strip(const StepArgs &a, cudaStream_t st);
+int launch_convert_strip(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st);
+int launch_diff_strip(const DiffArgs &a, cudaStream_t st);
 
 // any width % 4 == 0 / height % 2 == 0 (legacy geometry that is not a multiple of 16)
 int launch_convert_generic(int w, int h, const uint8_t *y, const uint8_t *u, const uint8_t *v,

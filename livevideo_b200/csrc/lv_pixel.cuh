@@ -26,16 +26,29 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     return __byte_perm(a, b, sel);
 }
 
-// byte k (0..3) of w, zero extended.  IDP.4A with a one-hot byte selector: the dot-product unit sits on
-// the FMA pipe, so the 48 byte extractions per 32 pixels stay off the ALU pipe (PRMT/LOP3/SHF/VIADDMNMX)
-// that bounds this kernel (measured: tools/ubench/pipes.cu).
+// Two instruction-mix switches, chosen by measurement (tools/ubench/pipes.cu shows PRMT/SHF/LOP3/VIADDMNMX on
+// the ALU pipe and IMAD/IDP on the FMA pipe, 2 warp-instructions/clk/SM each; profiles/ has the A/B runs):
+//   LV_EXTRACT_IDP : byte extraction with IDP.4A (FMA pipe) instead of PRMT (ALU pipe)
+//   LV_CHAN_HI     : channel value moved to the high byte of each halfword with *128 (IMAD.SHL, FMA pipe)
+//                    instead of >>1 into the low byte (SHF, ALU pipe)
+#ifndef LV_EXTRACT_IDP
+#define LV_EXTRACT_IDP 0
+#endif
+#ifndef LV_CHAN_HI
+#define LV_CHAN_HI 0
+#endif
+#ifndef LV_DIFF_POPC
+#define LV_DIFF_POPC 0
+#endif
+
+// byte k (0..3) of w, zero extended
 template <int K>
 __device__ __forceinline__ int ubyte(uint32_t w)
 {
-#ifdef LV_UBYTE_PRMT
-    return (int)prmt(w, 0u, 0x4440u | (uint32_t)K);
-#else
+#if LV_EXTRACT_IDP
     return (int)__dp4a(w, 1u << (8 * K), 0u);
+#else
+    return (int)prmt(w, 0u, 0x4440u | (uint32_t)K);
 #endif
 }
 
@@ -66,14 +79,21 @@ __device__ __forceinline__ uint32_t luma_pair(int ya, int yb)
     return prmt((uint32_t)TA, (uint32_t)TB, 0x7632u);
 }
 
-// add + clamp to [0,511] per halfword (one VIADDMNMX), then *128: the channel value x>>1 lands in the
-// HIGH byte of each halfword (bytes 1 and 3); the low bytes hold only the discarded bit and are never
-// selected.  The multiply is an IMAD, i.e. it runs on the FMA pipe instead of the ALU pipe (SHF) that
-// bounds this kernel.
+// add + clamp to [0,511] per halfword (one VIADDMNMX.S16x2.RELU), then drop the low bit:
+//   LV_CHAN_HI = 0: >>1, the channel value is the LOW byte of each halfword (bytes 0 and 2; bit 15 may carry
+//                   the upper halfword's dropped bit, it is never selected)
+//   LV_CHAN_HI = 1: *128, the channel value is the HIGH byte of each halfword (bytes 1 and 3)
 __device__ __forceinline__ uint32_t chan_pair(uint32_t t2, uint32_t c2)
 {
+#if LV_CHAN_HI
     return __viaddmin_s16x2_relu(t2, c2, 0x01ff01ffu) * 128u;
+#else
+    return __viaddmin_s16x2_relu(t2, c2, 0x01ff01ffu) >> 1;
+#endif
 }
+// the two channel bytes of a chan_pair() result (even pixel, odd pixel)
+__device__ __forceinline__ uint8_t chan_even(uint32_t c) { return (uint8_t)(c >> (LV_CHAN_HI ? 8 : 0)); }
+__device__ __forceinline__ uint8_t chan_odd(uint32_t c) { return (uint8_t)(c >> (LV_CHAN_HI ? 24 : 16)); }
 
 // 4 pixels (one 32-bit word of luma, two chroma samples) -> 12 bytes B,G,R,B,G,R,...
 __device__ __forceinline__ void convert4(uint32_t yw, const Chroma2 &c0, const Chroma2 &c1,
@@ -83,10 +103,17 @@ __device__ __forceinline__ void convert4(uint32_t yw, const Chroma2 &c0, const C
     const uint32_t tb = luma_pair(ubyte<2>(yw), ubyte<3>(yw));
     const uint32_t Ba = chan_pair(ta, c0.cb2), Ga = chan_pair(ta, c0.ng2), Ra = chan_pair(ta, c0.cr2);
     const uint32_t Bb = chan_pair(tb, c1.cb2), Gb = chan_pair(tb, c1.ng2), Rb = chan_pair(tb, c1.cr2);
+#if LV_CHAN_HI
     // pixel p of pair x sits in byte 1 (even) / byte 3 (odd) of Bx,Gx,Rx
     o0 = prmt(prmt(Ba, Ga, 0x3051u), Ra, 0x3510u);                       // b0 g0 r0 b1
     o1 = prmt(prmt(prmt(Ga, Ra, 0x0073u), Bb, 0x0510u), Gb, 0x5210u);    // g1 r1 b2 g2
     o2 = prmt(prmt(Rb, Bb, 0x3071u), Gb, 0x3710u);                       // r2 b3 g3 r3
+#else
+    // pixel p of pair x sits in byte 0 (even) / byte 2 (odd) of Bx,Gx,Rx
+    o0 = prmt(prmt(Ba, Ga, 0x2040u), Ra, 0x3410u);                       // b0 g0 r0 b1
+    o1 = prmt(prmt(prmt(Ga, Ra, 0x0062u), Bb, 0x0410u), Gb, 0x4210u);    // g1 r1 b2 g2
+    o2 = prmt(prmt(Rb, Bb, 0x2060u), Gb, 0x3610u);                       // r2 b3 g3 r3
+#endif
 }
 
 // per-byte (|a-b| > tol) for 4 pixels: returns a word whose bit 7 of byte k is the result for
@@ -119,6 +146,14 @@ __device__ __forceinline__ uint32_t diff_mask16(const uint4 &cur, const uint4 &r
 __device__ __forceinline__ uint32_t diff_count16(const uint4 &cur, const uint4 &ref, uint32_t tol4, uint32_t ntol7,
                                                  uint32_t acc)
 {
+#if LV_DIFF_POPC
+    // all-ALU variant: OR the four compare words into distinct bit positions, one POPC
+    const uint32_t r0 = diff_gt4(cur.x, ref.x, tol4, ntol7) & 0x80808080u;
+    const uint32_t r1 = diff_gt4(cur.y, ref.y, tol4, ntol7) & 0x80808080u;
+    const uint32_t r2 = diff_gt4(cur.z, ref.z, tol4, ntol7) & 0x80808080u;
+    const uint32_t r3 = diff_gt4(cur.w, ref.w, tol4, ntol7) & 0x80808080u;
+    return acc + ((uint32_t)__popc(r0 | (r1 >> 1) | (r2 >> 2) | (r3 >> 3)) << 7);
+#endif
     acc = __dp4a(diff_gt4(cur.x, ref.x, tol4, ntol7) & 0x80808080u, 0x01010101u, acc);
     acc = __dp4a(diff_gt4(cur.y, ref.y, tol4, ntol7) & 0x80808080u, 0x01010101u, acc);
     acc = __dp4a(diff_gt4(cur.z, ref.z, tol4, ntol7) & 0x80808080u, 0x01010101u, acc);

@@ -57,7 +57,7 @@ struct TArgs {
     int tol, mb_thresh;
     int n_items;            // total_frames * mb_h * xt
     int dx, dmby, df;       // (number of warps in the grid) written in (x, mby, frame) digits
-    int dbg;
+    int n_sm;               // CTAs are renumbered so that the CTAs resident on one SM work on adjacent items
     uint16_t *mask_bits;
     uint8_t *mask_bytes;
     uint16_t *mb_count;
@@ -72,9 +72,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 // instructions get their uniform-register operands without a per-lane waterfall loop
 __device__ __forceinline__ bool elect_one()
 {
-#ifdef LV_NO_ELECT
-    return (threadIdx.x & 31) == 0;
-#endif
     uint32_t pred;
     asm volatile(
         "{\n"
@@ -228,7 +225,14 @@ k_tma(const __grid_constant__ Maps m, const TArgs a)
     const int G = (int)gridDim.x * kWarps;
     Walk cons;
     {
-        const int g = (int)blockIdx.x * kWarps + warp;
+        // CTA b lands on SM b % n_sm (first wave, round-robin): give co-resident CTAs neighbouring items so
+        // that one SM's TMA traffic stays within a few pages
+        int vb = (int)blockIdx.x;
+        if (a.n_sm > 0) {
+            const int per = (int)gridDim.x / a.n_sm;                 // CTAs per SM (grid is a multiple of n_sm)
+            vb = ((int)blockIdx.x % a.n_sm) * per + (int)blockIdx.x / a.n_sm;
+        }
+        const int g = vb * kWarps + warp;
         const int per_frame = a.mb_h * a.xt;
         cons.item = g;
         cons.f = g / per_frame;
@@ -295,7 +299,7 @@ k_tma(const __grid_constant__ Maps m, const TArgs a)
                 }
             }
 
-            if (kConv && !(a.dbg & 8)) {
+            if (kConv) {
                 const uint2 uu = lds8(in + uv_off);
                 const uint2 vv = lds8(in + uv_off + 256u);
                 Chroma2 c[8];
@@ -324,7 +328,7 @@ k_tma(const __grid_constant__ Maps m, const TArgs a)
                 sts16(o_row0 - 384u, s0); sts16(o_row0 - 384u + 16, s1); sts16(o_row0 - 384u + 32, s2);
                 fence_proxy_async();          // generic-proxy writes -> visible to the TMA store
                 __syncwarp();
-                if (!(a.dbg & 1) && elect_one()) {
+                if (elect_one()) {
                     // destination rows h-1-(y0+7) .. h-1-y0 (bottom-up DIB, Convert.obj .text+0x350..0x39f);
                     // a band that is only partly inside the frame is handled below
                     const int dst0 = a.h - 8 - y0;
@@ -340,7 +344,7 @@ k_tma(const __grid_constant__ Maps m, const TArgs a)
                 }
             }
 
-            if (kDiff && a.has_state_out && !(a.dbg & 2) && cons.t == a.n_frames - 1) {
+            if (kDiff && a.has_state_out && cons.t == a.n_frames - 1) {
                 // prev_frm <- curr_frm (lib/JM/image.c:1553-1561): the band just consumed is the new state
                 __syncwarp();
                 if (elect_one()) {
@@ -351,7 +355,7 @@ k_tma(const __grid_constant__ Maps m, const TArgs a)
             }
         }
 
-        if (kDiff && !(a.dbg & 4)) {
+        if (kDiff) {
             uint32_t tot = cnt;
             tot += __shfl_xor_sync(0xffffffffu, tot, 8);
             tot += __shfl_xor_sync(0xffffffffu, tot, 16);
@@ -445,7 +449,7 @@ int launch_k(const Maps &m, const TArgs &a, int sm_count, cudaStream_t st)
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
     TArgs b = a;
-    { const char *e = getenv("LV_TMA_DEBUG"); b.dbg = e ? atoi(e) : 0; }
+    b.n_sm = ctas == max_ctas ? sm_count : 0;
     {   // the warp count of the grid in (x, mby, frame) digits: the kernel walks items without dividing
         const long long G = ctas * kWarps, per_frame = (long long)a.mb_h * a.xt;
         b.df = (int)(G / per_frame);

@@ -312,6 +312,42 @@ def test_errors_are_codes_not_crashes(lv, torch_cuda):
     assert L.lv_create(99, 352, 288, 1, 20, 0, C.byref(h)) == -3
 
 
+# ---- every kernel variant computes the same bytes --------------------------------------------------------------
+
+@pytest.mark.parametrize("variant", ["tile", "tma", "strip"])
+def test_kernel_variants_are_bit_identical(lv, orc, torch_cuda, variant):
+    """tile (default), TMA pipeline and register-pipelined strips, over aligned, ragged and partial-band geometries,
+    with and without the mask outputs, plus the conversion-only and difference-only entries."""
+    torch = torch_cuda
+    lv.set_kernel_variant(variant)
+    try:
+        assert lv.get_kernel_variant() == variant
+        for (w, h, ns, nf) in [(1920, 1080, 1, 3), (352, 288, 2, 3), (1280, 720, 3, 2), (96, 20, 2, 2), (64, 18, 1, 3),
+                               (4096, 24, 1, 2), (160, 8, 2, 2), (48, 18, 1, 2)]:
+            frames = orc.gen_batch("camera" if min(w, h) >= 16 else "uniform", 5, ns, nf, w, h)
+            prev = np.zeros((ns, w * h), np.uint8)
+            ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, 20, 0)
+            for masks in (True, False):
+                got = run_fused(lv, torch, frames, ns, nf, w, h, 20, 0, masks=masks)
+                assert_matches_oracle(orc, got, ref, w, h, ns * nf, masks=masks)
+                assert np.array_equal(got["state"], prev), (variant, w, h)
+            ctx = lv.Context(w, h)
+            d_out = torch.empty(ns * nf * ctx.bgr_bytes, dtype=torch.uint8, device="cuda")
+            ctx.convert_batch(torch.from_numpy(frames.reshape(-1)).cuda(), ns * nf, d_out)
+            assert np.array_equal(d_out.cpu().numpy(), ref["bgr"]), (variant, "convert", w, h)
+            cur = np.ascontiguousarray(frames[:, :, :w * h]).reshape(-1)
+            refy = np.roll(cur, 7)
+            out = ctx.alloc_outputs(ns * nf, bgr=False)
+            ctx.diff_batch(torch.from_numpy(cur).cuda(), torch.from_numpy(refy).cuda(), ns * nf, out)
+            torch.cuda.synchronize()
+            for i in range(ns * nf):
+                _, cnt, mp, _ = orc.frame_diff_mb(cur[i * w * h:(i + 1) * w * h], refy[i * w * h:(i + 1) * w * h], w, h, 20, 0)
+                assert np.array_equal(out["mb_count"].cpu().numpy().view(np.uint16)[i * ctx.mbs:(i + 1) * ctx.mbs], cnt)
+            ctx.close()
+    finally:
+        lv.set_kernel_variant("tile")
+
+
 # ---- BASELINE.json configurations at full size --------------------------------------------------------------
 
 def _full_size(lv, orc, torch, w, h, ns, nf, kind="camera"):
