@@ -23,6 +23,42 @@ __global__ void __launch_bounds__(256) k_mix(const uint4 *__restrict__ y, const 
     uint4 q = make_uint4(b.x, b.y, a.x ^ b.x, a.y);
     __stcs(out + 3 * i, a); __stcs(out + 3 * i + 1, q); __stcs(out + 3 * i + 2, a);
 }
+// two-row variant: a thread handles group i of an even row and of the odd row below it (row pitch W groups),
+// exactly like the real kernel's 16 px x 2 rows patch; same total bytes
+__global__ void __launch_bounds__(256) k_mix2(const uint4 *__restrict__ y, const uint2 *__restrict__ c, uint4 *__restrict__ out,
+                                               size_t n_pairs, int W)
+{
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;     // index over (row pair, group)
+    if (i >= n_pairs) return;
+    const size_t rp = i / W, gx = i - rp * W;
+    const size_t i0 = (2 * rp) * W + gx, i1 = i0 + W;
+    uint4 a0 = __ldg(y + i0), a1 = __ldg(y + i1);
+    uint2 b0 = __ldcs(c + rp * W + gx), b1 = __ldcs(c + n_pairs + rp * W + gx);   // "U" and "V" planes, 8 B each
+    uint4 q = make_uint4(b0.x, b0.y, b1.x, b1.y);
+    __stcs(out + 3 * i0, a0); __stcs(out + 3 * i0 + 1, q); __stcs(out + 3 * i0 + 2, a0);
+    __stcs(out + 3 * i1, a1); __stcs(out + 3 * i1 + 1, q); __stcs(out + 3 * i1 + 2, a1);
+}
+// V1: 2-row loads, flat stores (96 contiguous bytes per thread).  V2: flat loads (32 contiguous bytes), 2-row stores.
+template <int V>
+__global__ void __launch_bounds__(256) k_mixv(const uint4 *__restrict__ y, const uint2 *__restrict__ c, uint4 *__restrict__ out,
+                                               size_t n_pairs, int W)
+{
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_pairs) return;
+    const size_t rp = i / W, gx = i - rp * W;
+    const size_t i0 = (2 * rp) * W + gx, i1 = i0 + W;
+    uint4 a0, a1;
+    if (V == 1) { a0 = __ldg(y + i0); a1 = __ldg(y + i1); } else { a0 = __ldg(y + 2 * i); a1 = __ldg(y + 2 * i + 1); }
+    uint2 b0 = __ldcs(c + i), b1 = __ldcs(c + n_pairs + i);
+    uint4 q = make_uint4(b0.x, b0.y, b1.x, b1.y);
+    if (V == 1) {
+        uint4 *o = out + 6 * i;
+        __stcs(o, a0); __stcs(o + 1, q); __stcs(o + 2, a0); __stcs(o + 3, a1); __stcs(o + 4, q); __stcs(o + 5, a1);
+    } else {
+        __stcs(out + 3 * i0, a0); __stcs(out + 3 * i0 + 1, q); __stcs(out + 3 * i0 + 2, a0);
+        __stcs(out + 3 * i1, a1); __stcs(out + 3 * i1 + 1, q); __stcs(out + 3 * i1 + 2, a1);
+    }
+}
 template <typename F>
 float timeit(F f)
 {
@@ -52,5 +88,11 @@ int main()
     // previous-frame luma = same array shifted by one 1080p frame (2 MB): hits L2
     t = timeit([&] { k_mix<true><<<blocks, 256>>>(y + 2073600 / 16, c, y, out, groups - 2073600 / 16); });
     printf("flat mix 1.5r:3w + 1 L2 read: %7.1f us  %6.0f GB/s DRAM  %6.0f GB/s 'algorithmic 5.5 B/px'\n", t, px * 4.5 / t / 1e3, px * 5.5 / t / 1e3);
+    t = timeit([&] { k_mix2<<<(unsigned)((groups / 2 + 255) / 256), 256>>>(y, c, out, groups / 2, 120); });
+    printf("flat mix, 2 rows per thread : %7.1f us  %6.0f GB/s DRAM  %6.0f GB/s 'algorithmic 5.5 B/px'\n", t, px * 4.5 / t / 1e3, px * 5.5 / t / 1e3);
+    t = timeit([&] { k_mixv<1><<<(unsigned)((groups / 2 + 255) / 256), 256>>>(y, c, out, groups / 2, 120); });
+    printf("V1 2-row loads, flat stores : %7.1f us\n", t);
+    t = timeit([&] { k_mixv<2><<<(unsigned)((groups / 2 + 255) / 256), 256>>>(y, c, out, groups / 2, 120); });
+    printf("V2 flat loads, 2-row stores : %7.1f us\n", t);
     return 0;
 }
