@@ -242,6 +242,12 @@ def run_ours(args):
 
     def step():
         return sc.step(d_in, nf, out, gather=world > 1)
+    if world > 1:
+        # every rank must see every stream's summary: check the gathered table once against the local block
+        full = step()
+        torch.cuda.synchronize()
+        mine = out["summary"][: n * 2].reshape(ns, nf, 2)
+        assert torch.equal(full[sc.first_stream:sc.first_stream + ns], mine), "summary all-gather mismatch"
 
     def barrier():
         if world > 1:
@@ -255,13 +261,18 @@ def run_ours(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
     launches0 = ctx.kernel_launches
     sampler.start()
+    pending = None
     for i in range(args.steps):
         ev[2 * i].record()
-        ctx.convert_diff_batch(d_in, ns, nf, out)
-        ev[2 * i + 1].record()
         if world > 1:
-            from livevideo_b200.shard import gather_summaries
-            gather_summaries(out["summary"][: n * 2], total_streams, nf)
+            # kernel + summary all-gather; the gather of step i overlaps the kernel of step i+1
+            pending = sc.step_async(d_in, nf, out)
+        else:
+            ctx.convert_diff_batch(d_in, ns, nf, out)
+        ev[2 * i + 1].record()
+    if pending is not None:
+        gathered = pending.result()          # the last gather is inside the timed region
+        assert gathered.shape == (total_streams, nf, 2)
     sampler.sample()
     barrier()
     sampler.stop()

@@ -35,6 +35,46 @@ def max_shard(n_streams: int, world: int) -> int:
     return max(shard_range(n_streams, world, r)[1] for r in range(world))
 
 
+class PendingGather:
+    """Handle of an in-flight summary all-gather; result() waits and returns [n_streams, n_frames, 2]."""
+
+    def __init__(self, work, out, n_streams, n_frames, world, cap):
+        self.work, self.out = work, out
+        self.n_streams, self.n_frames, self.world, self.cap = n_streams, n_frames, world, cap
+
+    def result(self):
+        import torch
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        out = self.out.reshape(self.world, self.cap, self.n_frames, 2)
+        parts = [out[r, :shard_range(self.n_streams, self.world, r)[1]] for r in range(self.world)]
+        return torch.cat(parts, dim=0)
+
+
+def gather_summaries_async(local_summary, n_streams: int, n_frames: int, group=None, staging=None, out=None):
+    """Start the all-gather and return a PendingGather without making the compute stream wait for it.
+
+    The local summaries are first copied into `staging` (so the caller may overwrite `local_summary` with the
+    next step right away); the collective then runs on NCCL's own stream behind that copy, overlapped with
+    the next fused kernel.  `staging`/`out` let the caller reuse buffers (ping-pong across steps)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    first, count = shard_range(n_streams, world, rank)
+    cap = max_shard(n_streams, world)
+    local = local_summary.reshape(-1)
+    if local.numel() != count * n_frames * 2:
+        raise ValueError(f"rank {rank}: expected {count * n_frames * 2} summary words, got {local.numel()}")
+    if staging is None:
+        staging = torch.zeros(cap * n_frames * 2, dtype=local.dtype, device=local.device)
+    if out is None:
+        out = torch.empty(world * cap * n_frames * 2, dtype=local.dtype, device=local.device)
+    staging[: local.numel()].copy_(local)
+    work = dist.all_gather_into_tensor(out, staging, group=group, async_op=True)
+    return PendingGather(work, out, n_streams, n_frames, world, cap)
+
+
 def gather_summaries(local_summary, n_streams: int, n_frames: int, group=None):
     """All-gather the per-(stream, frame) summaries.
 
@@ -71,6 +111,10 @@ class ShardedContext:
         self.first_stream, self.local_streams = shard_range(total_streams, world, rank)
         self.device = rank if device is None else device
         self.ctx = Context(width, height, max(self.local_streams, 1), tol, mb_thresh, device=self.device)
+        self._pending = [None, None]      # ping-pong: the gather of step k overlaps the kernel of step k+1
+        self._staging = [None, None]
+        self._gathered = [None, None]
+        self._k = 0
 
     def step(self, i420_local, n_frames, out, cuda_stream=None, gather=True, group=None):
         """Fused kernel over this rank's streams, then (optionally) the summary all-gather.
@@ -80,3 +124,26 @@ class ShardedContext:
             return gather_summaries(out["summary"][: self.local_streams * n_frames * 2], self.total_streams,
                                     n_frames, group=group)
         return None
+
+    def step_async(self, i420_local, n_frames, out, group=None):
+        """Fused kernel, then the summary all-gather started WITHOUT blocking the compute stream: the returned
+        PendingGather completes while the next step's kernel runs.  At most two gathers are in flight; the one
+        from two steps ago is waited for before its buffers are reused."""
+        import torch
+        import torch.distributed as dist
+        self.ctx.convert_diff_batch(i420_local, self.local_streams, n_frames, out)
+        local = out["summary"][: self.local_streams * n_frames * 2]
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return PendingGather(None, local.clone(), self.total_streams, n_frames, 1, self.total_streams)
+        i = self._k & 1
+        self._k += 1
+        if self._pending[i] is not None and self._pending[i].work is not None:
+            self._pending[i].work.wait()
+        cap = max_shard(self.total_streams, self.world)
+        need = cap * n_frames * 2
+        if self._staging[i] is None or self._staging[i].numel() != need:
+            self._staging[i] = torch.zeros(need, dtype=local.dtype, device=local.device)
+            self._gathered[i] = torch.empty(self.world * need, dtype=local.dtype, device=local.device)
+        self._pending[i] = gather_summaries_async(local, self.total_streams, n_frames, group=group,
+                                                  staging=self._staging[i], out=self._gathered[i])
+        return self._pending[i]

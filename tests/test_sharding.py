@@ -59,6 +59,10 @@ def _worker(rank, world, port, n_streams, n_frames, w, h, q):
         r = orc.convert_diff_batch(frames, prev, count, n_frames, w, h, 20, 0, want_bgr=False, want_mask=False)
         local = torch.from_numpy(r["summary"].astype(np.int64).astype(np.int32).reshape(-1))
         full = gather_summaries(local, n_streams, n_frames)
+        from livevideo_b200.shard import gather_summaries_async
+        pend = [gather_summaries_async(local, n_streams, n_frames) for _ in range(3)]   # several in flight
+        for p in pend:
+            assert torch.equal(p.result(), full)
         q.put((rank, full.numpy().copy()))
     finally:
         dist.destroy_process_group()
