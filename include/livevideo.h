@@ -116,6 +116,20 @@ LV_API int lv_diff_batch(lv_ctx *ctx, const uint8_t *d_cur_y, const uint8_t *d_r
                          uint16_t *d_mask_bits, uint8_t *d_mask_bytes, uint16_t *d_mb_count,
                          uint8_t *d_mb_map, uint32_t *d_summary, void *cuda_stream);
 
+/* ---- the steps beside / after the fused path that the application shows ----------
+ * lv_write_bks: the literal CMainDlg::WriteBks (MainDlg.cpp:771-835): for every sample of n_frames I420 frames,
+ *   out = IsNearlyZero(cur - bkd, tol) ? fill : cur, fill = 16 (Y) / 128 (U, V), against ONE background frame
+ *   d_bkd_i420 (MainDlg.cpp:238-246).  d_obj_bits (optional, width % 16 == 0) receives bkd_obj
+ *   (lib/JM/image.c:4798,4803) as a luma bit mask in the d_mask_bits layout.  tol in [0,255] (the reference uses 25
+ *   here, MainDlg.cpp:780, and BKD_STR_TOL = 20 in image.c:4698).
+ * lv_object_box: min/max x,y of the set mask pixels inside the window [x0..x1] x [y0..y1] (inclusive) of ONE
+ *   frame (lib/JM/image.c:4818-4838); d_box4 = {min_x, max_x, min_y, max_y}; an empty window gives
+ *   {x1+1, x0-1, y1+1, y0-1}, the reference's initial values.  mask_is_bits selects the d_mask_bits layout. */
+LV_API int lv_write_bks(lv_ctx *ctx, const uint8_t *d_cur_i420, const uint8_t *d_bkd_i420, int n_frames, int tol,
+                        uint8_t *d_out_i420, uint16_t *d_obj_bits, void *cuda_stream);
+LV_API int lv_object_box(lv_ctx *ctx, const void *d_mask, int mask_is_bits, int x0, int x1, int y0, int y1,
+                         int *d_box4, void *cuda_stream);
+
 /* ---- host-buffer step: pinned, double-buffered H2D -> fused kernel -> D2H ------------------------
  * The call a host application makes when frames live in host memory (the JM producer hook of
  * lib/JM/output.c:427-451 writes into the pinned input).  lv_host_alloc / lv_host_free hand out

@@ -210,6 +210,27 @@ class Context:
             _dev_ptr(out.get("summary"), torch.int32, n_frames * 2, "summary", d), _stream_handle(cuda_stream)),
             "lv_diff_batch")
 
+    def write_bks(self, cur_i420, bkd_i420, n_frames, out_i420, tol=25, obj_bits=None, cuda_stream=None):
+        """The reference's WriteBks (MainDlg.cpp:771-835): background-subtracted I420 frames (device tensors)."""
+        import torch
+        d = self.device
+        capi.check(capi.lib().lv_write_bks(
+            self._h, _dev_ptr(cur_i420, torch.uint8, n_frames * self.frame_bytes, "cur_i420", d),
+            _dev_ptr(bkd_i420, torch.uint8, self.frame_bytes, "bkd_i420", d), n_frames, tol,
+            _dev_ptr(out_i420, torch.uint8, n_frames * self.frame_bytes, "out_i420", d),
+            _dev_ptr(obj_bits, torch.int16, n_frames * self.mask_units, "obj_bits", d), _stream_handle(cuda_stream)),
+            "lv_write_bks")
+
+    def object_box(self, mask, x0, x1, y0, y1, mask_is_bits=False, cuda_stream=None):
+        """(min_x, max_x, min_y, max_y) of the set mask pixels inside the window (lib/JM/image.c:4818-4838)."""
+        import torch
+        box = torch.empty(4, dtype=torch.int32, device=torch.device("cuda", self.device))
+        need = self.mask_units if mask_is_bits else self.px
+        capi.check(capi.lib().lv_object_box(
+            self._h, _dev_ptr(mask, torch.int16 if mask_is_bits else torch.uint8, need, "mask", self.device),
+            1 if mask_is_bits else 0, x0, x1, y0, y1, box.data_ptr(), _stream_handle(cuda_stream)), "lv_object_box")
+        return tuple(int(v) for v in box.cpu())
+
     # ---- host API ------------------------------------------------------------------------------------
     def step_host(self, i420, n_streams, n_frames, bgr=None, mask_bits=None, mb_count=None, mb_map=None,
                   summary=None, first_stream=0):

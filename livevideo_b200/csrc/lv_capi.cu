@@ -306,6 +306,28 @@ int lv_diff_batch(lv_ctx *c, const uint8_t *d_cur_y, const uint8_t *d_ref_y, int
     return launch_result(lv::launch_diff(a, st), c->launches);
 }
 
+int lv_write_bks(lv_ctx *c, const uint8_t *d_cur, const uint8_t *d_bkd, int n_frames, int tol, uint8_t *d_out,
+                 uint16_t *d_obj_bits, void *cuda_stream)
+{
+    if (!c || !d_cur || !d_bkd || !d_out || n_frames < 0 || tol < 0 || tol > 255) return LV_E_ARG;
+    if (d_obj_bits && c->g.w % 16 != 0) return LV_E_SIZE;
+    if (n_frames == 0) return LV_OK;
+    DeviceGuard guard(c->device);
+    return launch_result(lv::launch_write_bks(c->g, d_cur, d_bkd, n_frames, tol, d_out, d_obj_bits, (cudaStream_t)cuda_stream),
+                         c->launches);
+}
+
+int lv_object_box(lv_ctx *c, const void *d_mask, int mask_is_bits, int x0, int x1, int y0, int y1, int *d_box4,
+                  void *cuda_stream)
+{
+    if (!c || !d_mask || !d_box4) return LV_E_ARG;
+    if (x0 < 0 || y0 < 0 || x1 >= c->g.w || y1 >= c->g.h) return LV_E_ARG;
+    if (mask_is_bits && c->g.w % 16 != 0) return LV_E_SIZE;
+    DeviceGuard guard(c->device);
+    return launch_result(lv::launch_object_box(c->g.w, static_cast<const uint8_t *>(d_mask), mask_is_bits != 0, x0, x1, y0, y1,
+                                               d_box4, (cudaStream_t)cuda_stream), c->launches);
+}
+
 int lv_set_kernel_variant(int variant)
 {
     if (variant < 0 || variant > 2) return LV_E_ARG;

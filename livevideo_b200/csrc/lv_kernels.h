@@ -74,6 +74,11 @@ int launch_step_strip(const StepArgs &a, cudaStream_t st);
 int launch_convert_strip(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st);
 int launch_diff_strip(const DiffArgs &a, cudaStream_t st);
 
+// lv_aux.cu: background subtraction (WriteBks) and object box
+int launch_write_bks(const Geom &g, const uint8_t *cur, const uint8_t *bkd, int n_frames, int tol, uint8_t *out,
+                     uint16_t *obj_bits, cudaStream_t st);
+int launch_object_box(int w, const uint8_t *mask, bool bits, int x0, int x1, int y0, int y1, int *d_box, cudaStream_t st);
+
 // any width % 4 == 0 / height % 2 == 0 (legacy geometry that is not a multiple of 16)
 int launch_convert_generic(int w, int h, const uint8_t *y, const uint8_t *u, const uint8_t *v,
                            uint8_t *bgr, cudaStream_t st);

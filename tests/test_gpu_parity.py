@@ -312,6 +312,48 @@ def test_errors_are_codes_not_crashes(lv, torch_cuda):
     assert L.lv_create(99, 352, 288, 1, 20, 0, C.byref(h)) == -3
 
 
+# ---- WriteBks background subtraction and the object box ---------------------------------
+
+@pytest.mark.parametrize("w,h", [(352, 288), (1920, 1080), (320, 240), (20, 6), (4, 2), (1280, 720)])
+def test_write_bks_matches_reference_loops(lv, orc, torch_cuda, w, h):
+    torch = torch_cuda
+    rng = np.random.default_rng(w + h)
+    n = 3
+    fb = w * h * 3 // 2
+    bkd = rng.integers(0, 256, fb, dtype=np.uint8)
+    cur = np.clip(bkd.astype(int)[None] + rng.integers(-40, 41, (n, fb)), 0, 255).astype(np.uint8)
+    ctx = lv.Context(w, h)
+    for tol in (0, 20, 25, 255):
+        d_out = torch.empty(n * fb, dtype=torch.uint8, device="cuda")
+        bits = torch.zeros(n * ctx.mask_units, dtype=torch.int16, device="cuda") if w % 16 == 0 else None
+        ctx.write_bks(torch.from_numpy(cur.reshape(-1)).cuda(), torch.from_numpy(bkd).cuda(), n, d_out, tol=tol, obj_bits=bits)
+        got = d_out.cpu().numpy().reshape(n, fb)
+        for i in range(n):
+            assert np.array_equal(got[i], orc.write_bks(cur[i], bkd, w, h, tol)), (w, h, tol, i)
+            if bits is not None:
+                mask, _, _, _ = orc.frame_diff_mb(cur[i, :w * h], bkd[:w * h], w, h, tol, 0)
+                want = orc.pack_mask16(mask, w, h)
+                assert np.array_equal(bits.cpu().numpy().view(np.uint16)[i * ctx.mask_units:(i + 1) * ctx.mask_units], want)
+    ctx.close()
+
+
+def test_object_box_matches_reference_scan(lv, orc, torch_cuda):
+    torch = torch_cuda
+    w, h = 352, 288
+    rng = np.random.default_rng(9)
+    ctx = lv.Context(w, h)
+    for density in (0.0, 0.0005, 0.05):
+        mask = (rng.random(w * h) < density).astype(np.uint8)
+        bits = orc.pack_mask16(mask, w, h)
+        d_mask = torch.from_numpy(mask).cuda()
+        d_bits = torch.from_numpy(bits.view(np.int16)).cuda()
+        for (x0, x1, y0, y1) in [(0, w - 1, 0, h - 1), (10, 200, 5, 100), (17, 17, 40, 40), (300, 351, 250, 287)]:
+            want = orc.object_box(mask, w, x0, x1, y0, y1)
+            assert ctx.object_box(d_mask, x0, x1, y0, y1) == want
+            assert ctx.object_box(d_bits, x0, x1, y0, y1, mask_is_bits=True) == want
+    ctx.close()
+
+
 # ---- every kernel variant computes the same bytes --------------------------------------------------------------
 
 @pytest.mark.parametrize("variant", ["tile", "tma", "strip"])
