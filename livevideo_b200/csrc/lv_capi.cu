@@ -12,6 +12,10 @@
 #include <cstring>
 #include <new>
 
+#ifndef LV_HOST_CHUNK_MB_DEFAULT
+#define LV_HOST_CHUNK_MB_DEFAULT 16
+#endif
+
 namespace {
 
 thread_local char g_err[256] = "";
@@ -370,8 +374,14 @@ int lv_step_host(lv_ctx *c, const uint8_t *h_i420, int first_stream, int n_strea
     const lv::Geom &g = c->g;
     const size_t mbs = (size_t)g.mb_w * g.mb_h, units = (size_t)g.units * g.h;
 
-    // chunk = cf frames of every stream; aim at ~32 MiB of input per chunk, at least 1 frame
-    int cf = (int)(((size_t)32 << 20) / (g.frame * (size_t)n_streams));
+    // chunk = cf frames of every stream; aim at ~LV_HOST_CHUNK_MB MiB of input per chunk, at least 1 frame
+    static size_t chunk_bytes = 0;
+    if (!chunk_bytes) {
+        const char *e = getenv("LV_HOST_CHUNK_MB");
+        const long mb = e ? atol(e) : 0;
+        chunk_bytes = (size_t)(mb > 0 && mb <= 1024 ? mb : LV_HOST_CHUNK_MB_DEFAULT) << 20;
+    }
+    int cf = (int)(chunk_bytes / (g.frame * (size_t)n_streams));
     if (cf < 1) cf = 1;
     if (cf > n_frames) cf = n_frames;
     // a slot must hold one chunk; streams are cut too if even one frame of all streams is too large
