@@ -104,6 +104,8 @@ def gather_summaries(local_summary, n_streams: int, n_frames: int, group=None):
 class ShardedContext:
     """This rank's share of `total_streams` camera streams on its own GPU."""
 
+    RING = 8
+
     def __init__(self, width: int, height: int, total_streams: int, tol: int = 20, mb_thresh: int = 0,
                  rank: int = 0, world: int = 1, device: Optional[int] = None):
         from .api import Context
@@ -111,9 +113,11 @@ class ShardedContext:
         self.first_stream, self.local_streams = shard_range(total_streams, world, rank)
         self.device = rank if device is None else device
         self.ctx = Context(width, height, max(self.local_streams, 1), tol, mb_thresh, device=self.device)
-        self._pending = [None, None]      # ping-pong: the gather of step k overlaps the kernel of step k+1
-        self._staging = [None, None]
-        self._gathered = [None, None]
+        # ring of in-flight gathers: the gather of step k overlaps the kernels of steps k+1 .. k+RING-1 (an 8-rank
+        # all-gather of a few hundred bytes is pure latency, ~2 kernel times at 1080p x 64)
+        self._pending = [None] * self.RING
+        self._staging = [None] * self.RING
+        self._gathered = [None] * self.RING
         self._k = 0
 
     def step(self, i420_local, n_frames, out, cuda_stream=None, gather=True, group=None):
@@ -127,15 +131,15 @@ class ShardedContext:
 
     def step_async(self, i420_local, n_frames, out, group=None):
         """Fused kernel, then the summary all-gather started WITHOUT blocking the compute stream: the returned
-        PendingGather completes while the next step's kernel runs.  At most two gathers are in flight; the one
-        from two steps ago is waited for before its buffers are reused."""
+        PendingGather completes while the next steps' kernels run.  At most RING gathers are in flight; the one
+        issued RING steps ago is waited for before its buffers are reused."""
         import torch
         import torch.distributed as dist
         self.ctx.convert_diff_batch(i420_local, self.local_streams, n_frames, out)
         local = out["summary"][: self.local_streams * n_frames * 2]
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return PendingGather(None, local.clone(), self.total_streams, n_frames, 1, self.total_streams)
-        i = self._k & 1
+        i = self._k % self.RING
         self._k += 1
         if self._pending[i] is not None and self._pending[i].work is not None:
             self._pending[i].work.wait()
