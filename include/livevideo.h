@@ -150,6 +150,30 @@ LV_API int lv_step_host(lv_ctx *ctx, const uint8_t *h_i420, int first_stream, in
 LV_API int lv_gen_synthetic(int kind, uint32_t seed, uint32_t first_stream, uint32_t first_frame, int n_streams,
                             int n_frames, int width, int height, uint8_t *d_i420, void *cuda_stream);
 
+/* ---- multi-GPU from one host process: streams sharded by stream ID, no pixel ever crosses GPUs ---------------
+ * Device g (devices[g], or g when devices == NULL) owns the contiguous block of streams [g*S/G, (g+1)*S/G)
+ * (lv_shard_range).  lv_shard_step only enqueues one fused launch per device on that device's own stream, so the
+ * devices run concurrently; d_i420[g] / d_bgr[g] / d_mb_count[g] / d_mb_map[g] are pointers in device g's memory
+ * holding that block (same layouts as lv_convert_diff_batch; output arrays or entries may be NULL).
+ * lv_gather_summaries is the only exchange of the path: an NCCL all-gather (bound at run time from libnccl.so.2) of
+ * {changed_px, changed_mbs} per (stream, frame) of the LAST step -- every device ends with the whole table
+ * (lv_shard_gathered, padded per rank to the largest block) and, when h_summary != NULL, the unpadded
+ * [total_streams][n_frames][2] table is copied to the host (synchronises device 0's stream only).
+ * With one device no collective is issued.  Returns LV_E_STATE when NCCL is needed but cannot be loaded. */
+typedef struct lv_shard lv_shard;
+LV_API int lv_shard_create(int n_devices, const int *devices, int width, int height, int total_streams, int tol,
+                           int mb_thresh, lv_shard **out);
+LV_API void lv_shard_destroy(lv_shard *s);
+LV_API int lv_shard_device_count(const lv_shard *s);
+LV_API int lv_shard_range(const lv_shard *s, int rank, int *device, int *first_stream, int *n_streams);
+LV_API lv_ctx *lv_shard_ctx(lv_shard *s, int rank);        /* rank's own context (state get/set, other entries) */
+LV_API void *lv_shard_stream(lv_shard *s, int rank);       /* rank's cudaStream_t */
+LV_API int lv_shard_step(lv_shard *s, const uint8_t *const *d_i420, int n_frames, uint8_t *const *d_bgr,
+                         uint16_t *const *d_mb_count, uint8_t *const *d_mb_map);
+LV_API int lv_gather_summaries(lv_shard *s, uint32_t *h_summary);
+LV_API const uint32_t *lv_shard_gathered(lv_shard *s, int rank);
+LV_API int lv_shard_sync(lv_shard *s);
+
 /* ---- kernel variant (process-wide) -------------------------------------------------------------------
  * 0 = tiled kernel (default), 1 = TMA pipeline (cp.async.bulk.tensor loads/stores), 2 = register-pipelined
  * strips.  All variants are bit-identical; the choice only affects speed (DESIGN.md has the measurements). */

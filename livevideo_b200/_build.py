@@ -7,7 +7,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "liblivevideo.so")
-SOURCES = ["lv_kernels.cu", "lv_strip.cu", "lv_tma.cu", "lv_aux.cu", "lv_capi.cu", "lv_synth.cu"]
+SOURCES = ["lv_kernels.cu", "lv_strip.cu", "lv_tma.cu", "lv_aux.cu", "lv_shard.cu", "lv_capi.cu", "lv_synth.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     cmd = [nvcc_path(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
-           "-Xptxas", "-v" if verbose else "-O3", "-cudart", "shared", "-o", LIB_PATH] + \
+           "-Xptxas", "-v" if verbose else "-O3", "-cudart", "shared", "-ldl", "-o", LIB_PATH] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -36,6 +36,16 @@ SYMBOLS = {
     "lv_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "lv_host_free": (C.c_int, [_vp]),
     "lv_step_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lv_shard_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "lv_shard_destroy": (None, [_vp]),
+    "lv_shard_device_count": (C.c_int, [_vp]),
+    "lv_shard_range": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "lv_shard_ctx": (_vp, [_vp, C.c_int]),
+    "lv_shard_stream": (_vp, [_vp, C.c_int]),
+    "lv_shard_step": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "lv_gather_summaries": (C.c_int, [_vp, _vp]),
+    "lv_shard_gathered": (_vp, [_vp, C.c_int]),
+    "lv_shard_sync": (C.c_int, [_vp]),
     "lv_set_kernel_variant": (C.c_int, [C.c_int]),
     "lv_get_kernel_variant": (C.c_int, []),
     "lv_kernel_launches": (C.c_uint64, [_vp]),

@@ -151,3 +151,56 @@ class ShardedContext:
         self._pending[i] = gather_summaries_async(local, self.total_streams, n_frames, group=group,
                                                   staging=self._staging[i], out=self._gathered[i])
         return self._pending[i]
+
+
+class SingleProcessShard:
+    """lv_shard_*: all GPUs of the box driven from ONE process through the C ABI (NCCL all-gather of the summaries).
+    The torchrun deployment (ShardedContext, one process per GPU) is the same partition."""
+
+    def __init__(self, width, height, total_streams, devices, tol=20, mb_thresh=0):
+        import ctypes as C
+
+        from . import capi
+        self._C, self._capi = C, capi
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        capi.check(capi.lib().lv_shard_create(len(devices), devs, width, height, total_streams, tol, mb_thresh,
+                                              C.byref(self._h)), "lv_shard_create")
+        self.devices, self.total_streams = list(devices), total_streams
+        self.ranges = []
+        for r in range(len(devices)):
+            d, f, n = C.c_int(), C.c_int(), C.c_int()
+            capi.check(capi.lib().lv_shard_range(self._h, r, C.byref(d), C.byref(f), C.byref(n)), "lv_shard_range")
+            self.ranges.append((d.value, f.value, n.value))
+
+    def close(self):
+        if self._h:
+            self._capi.lib().lv_shard_destroy(self._h)
+            self._h = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _ptrs(self, tensors):
+        C = self._C
+        if tensors is None:
+            return None
+        return (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+    def step(self, i420, n_frames, bgr=None, mb_count=None, mb_map=None):
+        """i420 etc.: one CUDA tensor per device (on that device) holding that device's block of streams."""
+        self._capi.check(self._capi.lib().lv_shard_step(self._h, self._ptrs(i420), n_frames, self._ptrs(bgr),
+                                                        self._ptrs(mb_count), self._ptrs(mb_map)), "lv_shard_step")
+
+    def gather(self, n_frames):
+        """[total_streams, n_frames, 2] uint32 on the host (NCCL all-gather across the devices, then one D2H)."""
+        import numpy as np
+        out = np.zeros((self.total_streams, n_frames, 2), dtype=np.uint32)
+        self._capi.check(self._capi.lib().lv_gather_summaries(self._h, out.ctypes.data), "lv_gather_summaries")
+        return out
+
+    def sync(self):
+        self._capi.check(self._capi.lib().lv_shard_sync(self._h), "lv_shard_sync")

@@ -459,3 +459,44 @@ def test_virtual_ranks_on_one_gpu_equal_single_rank(lv, orc, torch_cuda):
             assert np.array_equal(o["mb_count"][:count * T * sc.ctx.mbs].cpu().numpy().reshape(count, T, -1),
                                   cnt_full[first:first + count])
         assert np.array_equal(np.concatenate(parts), full)
+
+
+def _single_process_shard(lv, orc, torch, devices, S=5, T=3, w=352, h=288):
+    from livevideo_b200.shard import SingleProcessShard
+    sh = SingleProcessShard(w, h, S, devices)
+    frames = orc.gen_batch("camera", 4, S, T, w, h)
+    prev = np.zeros((S, w * h), np.uint8)
+    ref = orc.convert_diff_batch(frames, prev, S, T, w, h, 20, 0, want_mask=False)
+    fb = w * h * 3 // 2
+    mbs = ((w + 15) // 16) * ((h + 15) // 16)
+    ins, bgrs, cnts, maps = [], [], [], []
+    for (dev, first, n) in sh.ranges:
+        d = torch.device("cuda", dev)
+        ins.append(torch.from_numpy(frames[first:first + n].reshape(-1).copy()).to(d) if n else None)
+        bgrs.append(torch.empty(max(n, 1) * T * 3 * w * h, dtype=torch.uint8, device=d))
+        cnts.append(torch.empty(max(n, 1) * T * mbs, dtype=torch.int16, device=d))
+        maps.append(torch.empty(max(n, 1) * T * mbs, dtype=torch.uint8, device=d))
+    for _ in range(2):                      # second step: frame 0 differenced against the carried state
+        sh.step(ins, T, bgrs, cnts, maps)
+        table = sh.gather(T)
+    sh.sync()
+    ref2 = orc.convert_diff_batch(frames, prev, S, T, w, h, 20, 0, want_mask=False)   # prev now holds the last luma
+    assert np.array_equal(table, ref2["summary"].reshape(S, T, 2))
+    for i, (dev, first, n) in enumerate(sh.ranges):
+        if n:
+            assert np.array_equal(bgrs[i][: n * T * 3 * w * h].cpu().numpy(), ref2["bgr"][first * T * 3 * w * h:(first + n) * T * 3 * w * h])
+            assert np.array_equal(cnts[i][: n * T * mbs].cpu().numpy().view(np.uint16), ref2["mb_count"][first * T * mbs:(first + n) * T * mbs])
+    sh.close()
+    return ref
+
+
+def test_single_process_shard_one_device(lv, orc, torch_cuda):
+    _single_process_shard(lv, orc, torch_cuda, [0])
+
+
+def test_single_process_shard_all_devices_nccl(lv, orc, torch_cuda):
+    n = torch_cuda.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2): NCCL cannot build a communicator over one device twice")
+    _single_process_shard(lv, orc, torch_cuda, list(range(n)))
+    _single_process_shard(lv, orc, torch_cuda, list(range(n)), S=1)      # more devices than streams: empty blocks
