@@ -137,6 +137,15 @@ LV_API int lv_object_box(lv_ctx *ctx, const void *d_mask, int mask_is_bits, int 
  * and overlaps the upload of chunk k+1 (copy stream) with the kernel of chunk k and the download of
  * chunk k-1.  Host pointers may also be ordinary pageable memory (slower: staged by the driver).
  * Outputs may be NULL.  Synchronous: returns when every output is in host memory. */
+/* The upload half on its own, for consumers that keep the BGR on the device: lv_upload_async copies n_frames_total
+ * I420 frames from (pinned) host memory into the context's device input slot `slot` (0 or 1, sized on demand) on the
+ * context's copy stream and returns the device pointer; lv_upload_wait makes `cuda_stream` wait for that slot's copy.
+ * Alternating slots double-buffers: upload batch k+1 into slot (k+1)&1 while the kernel of batch k reads slot k&1.
+ * A slot must not be re-uploaded before the kernel that read it has been enqueued-and-finished (lv_upload_async
+ * waits for the event the caller records with lv_upload_release). */
+LV_API int lv_upload_async(lv_ctx *ctx, const uint8_t *h_i420, int n_frames_total, int slot, const uint8_t **d_i420);
+LV_API int lv_upload_wait(lv_ctx *ctx, int slot, void *cuda_stream);
+LV_API int lv_upload_release(lv_ctx *ctx, int slot, void *cuda_stream);   /* call after enqueuing the slot's consumer */
 LV_API int lv_host_alloc(void **p, size_t bytes);
 LV_API int lv_host_free(void *p);
 LV_API int lv_step_host(lv_ctx *ctx, const uint8_t *h_i420, int first_stream, int n_streams, int n_frames,

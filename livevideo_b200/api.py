@@ -231,6 +231,22 @@ class Context:
             1 if mask_is_bits else 0, x0, x1, y0, y1, box.data_ptr(), _stream_handle(cuda_stream)), "lv_object_box")
         return tuple(int(v) for v in box.cpu())
 
+    def upload_async(self, i420_host, n_frames_total, slot):
+        """Pinned host -> device slot `slot` on the context's copy stream; returns a uint8 CUDA tensor view of the slot.
+        Pair with upload_wait(slot) before the consumer and upload_release(slot) after it (double buffering)."""
+        import torch
+        p = C.c_void_p()
+        nbytes = n_frames_total * self.frame_bytes
+        capi.check(capi.lib().lv_upload_async(self._h, _host_ptr(i420_host, np.uint8, nbytes, "i420_host"), n_frames_total,
+                                              slot, C.byref(p)), "lv_upload_async")
+        return _DevView(p.value, nbytes, self.device).tensor()
+
+    def upload_wait(self, slot, cuda_stream=None):
+        capi.check(capi.lib().lv_upload_wait(self._h, slot, _stream_handle(cuda_stream)), "lv_upload_wait")
+
+    def upload_release(self, slot, cuda_stream=None):
+        capi.check(capi.lib().lv_upload_release(self._h, slot, _stream_handle(cuda_stream)), "lv_upload_release")
+
     # ---- host API ------------------------------------------------------------------------------------
     def step_host(self, i420, n_streams, n_frames, bgr=None, mask_bits=None, mb_count=None, mb_map=None,
                   summary=None, first_stream=0):
@@ -244,6 +260,18 @@ class Context:
             p(bgr, np.uint8, n * self.bgr_bytes, "bgr"), p(mask_bits, np.uint16, 2 * n * self.mask_units, "mask_bits"),
             p(mb_count, np.uint16, 2 * n * self.mbs, "mb_count"), p(mb_map, np.uint8, n * self.mbs, "mb_map"),
             p(summary, np.uint32, 8 * n, "summary")), "lv_step_host")
+
+
+class _DevView:
+    """A torch uint8 tensor over device memory owned by the library (no copy), via __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes, device):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+        self._device = device
+
+    def tensor(self):
+        import torch
+        return torch.as_tensor(self, device=torch.device("cuda", self._device))
 
 
 class PinnedArray:

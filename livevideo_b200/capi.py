@@ -33,6 +33,9 @@ SYMBOLS = {
     "lv_diff_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lv_write_bks": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "lv_object_box": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "lv_upload_async": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "lv_upload_wait": (C.c_int, [_vp, C.c_int, _vp]),
+    "lv_upload_release": (C.c_int, [_vp, C.c_int, _vp]),
     "lv_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "lv_host_free": (C.c_int, [_vp]),
     "lv_step_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),

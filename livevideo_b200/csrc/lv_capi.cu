@@ -59,6 +59,12 @@ struct lv_ctx {
     uint32_t *d_sum[kSlots] = {};
     cudaEvent_t ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
     int slot_frames = 0;                      // capacity of one slot in frames
+    // stand-alone upload slots (lv_upload_async)
+    cudaStream_t s_upload = nullptr;
+    uint8_t *d_up[2] = {nullptr, nullptr};
+    size_t up_cap[2] = {0, 0};
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_up_free[2] = {nullptr, nullptr};
+    bool up_pending_free[2] = {false, false};
 };
 
 namespace {
@@ -196,6 +202,12 @@ void lv_destroy(lv_ctx *c)
     if (!c) return;
     DeviceGuard guard(c->device);
     free_pipeline(c);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->d_up[i]);
+        if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
+        if (c->ev_up_free[i]) cudaEventDestroy(c->ev_up_free[i]);
+    }
+    if (c->s_upload) cudaStreamDestroy(c->s_upload);
     cudaFree(c->state[0]);
     cudaFree(c->state[1]);
     delete c;
@@ -340,6 +352,55 @@ int lv_set_kernel_variant(int variant)
 }
 
 int lv_get_kernel_variant(void) { return lv::kernel_variant(); }
+
+int lv_upload_async(lv_ctx *c, const uint8_t *h_i420, int n_frames_total, int slot, const uint8_t **d_i420)
+{
+    if (!c || !h_i420 || !d_i420 || n_frames_total < 1 || slot < 0 || slot > 1) return LV_E_ARG;
+    DeviceGuard guard(c->device);
+    if (!c->s_upload) {
+        LV_CUDA(cudaStreamCreateWithFlags(&c->s_upload, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            LV_CUDA(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+            LV_CUDA(cudaEventCreateWithFlags(&c->ev_up_free[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t bytes = c->g.frame * (size_t)n_frames_total;
+    // the consumer of this slot's previous contents must be done before the slot is overwritten (or re-allocated)
+    if (c->up_pending_free[slot]) LV_CUDA(cudaStreamWaitEvent(c->s_upload, c->ev_up_free[slot], 0));
+    if (bytes > c->up_cap[slot]) {
+        if (c->up_pending_free[slot]) LV_CUDA(cudaEventSynchronize(c->ev_up_free[slot]));
+        LV_CUDA(cudaStreamSynchronize(c->s_upload));
+        cudaFree(c->d_up[slot]);
+        c->d_up[slot] = nullptr;
+        c->up_cap[slot] = 0;
+        LV_CUDA(cudaMalloc(&c->d_up[slot], bytes));
+        c->up_cap[slot] = bytes;
+    }
+    c->up_pending_free[slot] = false;
+    LV_CUDA(cudaMemcpyAsync(c->d_up[slot], h_i420, bytes, cudaMemcpyHostToDevice, c->s_upload));
+    LV_CUDA(cudaEventRecord(c->ev_up[slot], c->s_upload));
+    *d_i420 = c->d_up[slot];
+    return LV_OK;
+}
+
+int lv_upload_wait(lv_ctx *c, int slot, void *cuda_stream)
+{
+    if (!c || slot < 0 || slot > 1) return LV_E_ARG;
+    if (!c->s_upload) return LV_E_STATE;
+    DeviceGuard guard(c->device);
+    LV_CUDA(cudaStreamWaitEvent((cudaStream_t)cuda_stream, c->ev_up[slot], 0));
+    return LV_OK;
+}
+
+int lv_upload_release(lv_ctx *c, int slot, void *cuda_stream)
+{
+    if (!c || slot < 0 || slot > 1) return LV_E_ARG;
+    if (!c->s_upload) return LV_E_STATE;
+    DeviceGuard guard(c->device);
+    LV_CUDA(cudaEventRecord(c->ev_up_free[slot], (cudaStream_t)cuda_stream));
+    c->up_pending_free[slot] = true;
+    return LV_OK;
+}
 
 int lv_host_alloc(void **p, size_t bytes)
 {

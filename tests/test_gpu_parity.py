@@ -500,3 +500,30 @@ def test_single_process_shard_all_devices_nccl(lv, orc, torch_cuda):
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2): NCCL cannot build a communicator over one device twice")
     _single_process_shard(lv, orc, torch_cuda, list(range(n)))
     _single_process_shard(lv, orc, torch_cuda, list(range(n)), S=1)      # more devices than streams: empty blocks
+
+
+def test_upload_slots_double_buffering(lv, orc, torch_cuda):
+    """lv_upload_async / wait / release: host batches alternate between two device slots; results equal one big launch."""
+    torch = torch_cuda
+    w, h, T, B = 352, 288, 4, 5
+    frames = orc.gen_batch("camera", 6, 1, T * B, w, h)
+    prev = np.zeros((1, w * h), np.uint8)
+    ref = orc.convert_diff_batch(frames, prev, 1, T * B, w, h, 20, 0, want_mask=False)
+    ctx = lv.Context(w, h)
+    pins = [lv.pinned(T * ctx.frame_bytes) for _ in range(2)]
+    outs = [ctx.alloc_outputs(T) for _ in range(2)]
+    got_cnt, got_bgr = [], []
+    for b in range(B):
+        s = b & 1
+        if b >= 2:
+            torch.cuda.current_stream().synchronize()      # host buffer s is free again (its copy has completed)
+        pins[s].array[:] = frames[0, b * T:(b + 1) * T].reshape(-1)
+        d = ctx.upload_async(pins[s].array, T, s)
+        ctx.upload_wait(s)
+        ctx.convert_diff_batch(d, 1, T, outs[s])
+        ctx.upload_release(s)
+        got_cnt.append(outs[s]["mb_count"].cpu().numpy().view(np.uint16).copy())
+        got_bgr.append(outs[s]["bgr"].cpu().numpy().copy())
+    assert np.array_equal(np.concatenate(got_cnt), ref["mb_count"])
+    assert np.array_equal(np.concatenate(got_bgr), ref["bgr"])
+    ctx.close()
