@@ -68,6 +68,22 @@ LV_API void FrameDiff_MB(const unsigned char *cur_y, const unsigned char *ref_y,
                          int tol, int mb_thresh, unsigned char *mask, unsigned short *mb_count,
                          unsigned char *mb_map);
 
+/* The other five methods of ColorSpaceConversions (Convert.h:25-30; code at Convert.obj .text+0x1d0, +0x740, +0x8b0,
+ * +0x960, +0xa40).  The application never calls them; they complete the Convert.h surface with the object code's
+ * exact semantics (same host-pointer, synchronous, void convention as YV12_to_RGB24; w % 4 == 0, h % 4 == 0):
+ *   RGB24_to_YV12: in = bottom-up rows of R,G,B bytes; out = Y, Cb, Cr planes; chroma from the top-left pixel of each
+ *                  2x2 block; Y = sum of truncated 0.299/0.587/0.114 products (table-exact)
+ *   YVU9_to_YV12 : every input plane is read bottom-up; chroma (w/4 x h/4) replicated 2x2
+ *   YUY2_to_YV12 : Y0 U Y1 V rows -> Y plane, then the plane of the V bytes, then the plane of the U bytes; the odd
+ *                  row of each row pair supplies the chroma
+ *   YV12_to_YVU9 : luma copied, chroma point-sampled 2:1 in both directions
+ *   YV12_to_YUY2 : inverse layout of YUY2_to_YV12, one chroma row for both rows of a pair */
+LV_API void RGB24_to_YV12(unsigned char *in, unsigned char *out, int w, int h);
+LV_API void YVU9_to_YV12(unsigned char *in, unsigned char *out, int w, int h);
+LV_API void YUY2_to_YV12(unsigned char *in, unsigned char *out, int w, int h);
+LV_API void YV12_to_YVU9(unsigned char *in, unsigned char *out, int w, int h);
+LV_API void YV12_to_YUY2(unsigned char *in, unsigned char *out, int w, int h);
+
 /* ---- context API: device pointers, asynchronous on a caller-supplied CUDA stream ------------------ */
 typedef struct lv_ctx lv_ctx;
 
@@ -129,6 +145,11 @@ LV_API int lv_write_bks(lv_ctx *ctx, const uint8_t *d_cur_i420, const uint8_t *d
                         uint8_t *d_out_i420, uint16_t *d_obj_bits, void *cuda_stream);
 LV_API int lv_object_box(lv_ctx *ctx, const void *d_mask, int mask_is_bits, int x0, int x1, int y0, int y1,
                          int *d_box4, void *cuda_stream);
+
+/* Device-pointer form of the five converters above: kind 1 RGB24_to_YV12, 2 YVU9_to_YV12, 3 YUY2_to_YV12,
+ * 4 YV12_to_YVU9, 5 YV12_to_YUY2; n_frames frames back to back (bytes per frame: lv_format_bytes). */
+LV_API int lv_convert_format(lv_ctx *ctx, int kind, const uint8_t *d_in, uint8_t *d_out, int n_frames, void *cuda_stream);
+LV_API size_t lv_format_bytes(int kind, int width, int height, int output);
 
 /* ---- host-buffer step: pinned, double-buffered H2D -> fused kernel -> D2H ------------------------
  * The call a host application makes when frames live in host memory (the JM producer hook of

@@ -7,13 +7,10 @@
 // the same parameter lists (Convert.h:19-31), no data members and a trivial constructor (the original's
 // constructor only fills process-global tables, Convert.obj .text+0x000..0x1cf; the CUDA path needs none).
 //
-// Only YV12_to_RGB24 is ever called by the application; the other five converters are declared so that
-// existing code compiles, and report that they are not part of the B200 path if somebody calls them.
+// Only YV12_to_RGB24 is ever called by the application; the other five converters forward to their C entries too
+// (bit-exact with the object code, but simple kernels: they are not on the hot path).
 #ifndef LV_CONVERT_SHIM_HPP
 #define LV_CONVERT_SHIM_HPP
-
-#include <cstdio>
-#include <cstdlib>
 
 #include "livevideo.h"
 
@@ -28,19 +25,12 @@ public:
         ::YV12_to_RGB24(src0, src1, src2, dst_ori, width, height);
     }
 
-    void RGB24_to_YV12(unsigned char *, unsigned char *, int, int) { not_on_path("RGB24_to_YV12"); }
-    void YVU9_to_YV12(unsigned char *, unsigned char *, int, int) { not_on_path("YVU9_to_YV12"); }
-    void YUY2_to_YV12(unsigned char *, unsigned char *, int, int) { not_on_path("YUY2_to_YV12"); }
-    void YV12_to_YVU9(unsigned char *, unsigned char *, int, int) { not_on_path("YV12_to_YVU9"); }
-    void YV12_to_YUY2(unsigned char *, unsigned char *, int, int) { not_on_path("YV12_to_YUY2"); }
-
-private:
-    static void not_on_path(const char *name)
-    {
-        std::fprintf(stderr, "livevideo-b200: ColorSpaceConversions::%s is not part of the accelerated path "
-                             "(the application never calls it)\n", name);
-        std::abort();
-    }
+    // the five converters the application never calls; same object-code semantics, same signatures
+    void RGB24_to_YV12(unsigned char *in, unsigned char *out, int w, int h) { ::RGB24_to_YV12(in, out, w, h); }
+    void YVU9_to_YV12(unsigned char *in, unsigned char *out, int w, int h) { ::YVU9_to_YV12(in, out, w, h); }
+    void YUY2_to_YV12(unsigned char *in, unsigned char *out, int w, int h) { ::YUY2_to_YV12(in, out, w, h); }
+    void YV12_to_YVU9(unsigned char *in, unsigned char *out, int w, int h) { ::YV12_to_YVU9(in, out, w, h); }
+    void YV12_to_YUY2(unsigned char *in, unsigned char *out, int w, int h) { ::YV12_to_YUY2(in, out, w, h); }
 };
 
 #endif  // LV_CONVERT_SHIM_HPP

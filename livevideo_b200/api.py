@@ -49,10 +49,30 @@ class ColorSpaceConversions:
                                  _host_ptr(src2, np.uint8, px // 4, "src2"),
                                  _host_ptr(dst_ori, np.uint8, 3 * px, "dst_ori", True), width, height)
 
-    def _unused(self, *a, **k):
-        raise NotImplementedError("never called by the application (grep pCon. -> only YV12_to_RGB24); out of scope")
+    # the five methods the application never calls (Convert.h:25-30): same (in, out, w, h) convention, in place
+    def _fmt(self, name, kind, inp, out, w, h):
+        if w <= 0 or h <= 0:
+            return
+        if w % 4 or h % 4:
+            raise ValueError(f"{name} needs width % 4 == 0 and height % 4 == 0")
+        L = capi.lib()
+        getattr(L, name)(_host_ptr(inp, np.uint8, L.lv_format_bytes(kind, w, h, 0), "in"),
+                         _host_ptr(out, np.uint8, L.lv_format_bytes(kind, w, h, 1), "out", True), w, h)
 
-    RGB24_to_YV12 = YVU9_to_YV12 = YUY2_to_YV12 = YV12_to_YVU9 = YV12_to_YUY2 = _unused
+    def RGB24_to_YV12(self, inp, out, w, h):
+        self._fmt("RGB24_to_YV12", 1, inp, out, w, h)
+
+    def YVU9_to_YV12(self, inp, out, w, h):
+        self._fmt("YVU9_to_YV12", 2, inp, out, w, h)
+
+    def YUY2_to_YV12(self, inp, out, w, h):
+        self._fmt("YUY2_to_YV12", 3, inp, out, w, h)
+
+    def YV12_to_YVU9(self, inp, out, w, h):
+        self._fmt("YV12_to_YVU9", 4, inp, out, w, h)
+
+    def YV12_to_YUY2(self, inp, out, w, h):
+        self._fmt("YV12_to_YUY2", 5, inp, out, w, h)
 
 
 def FrameDiff_MB(cur_y, ref_y, width, height, tol=DEFAULT_TOL, mb_thresh=DEFAULT_MB_THRESH, mask=None,
@@ -246,6 +266,15 @@ class Context:
 
     def upload_release(self, slot, cuda_stream=None):
         capi.check(capi.lib().lv_upload_release(self._h, slot, _stream_handle(cuda_stream)), "lv_upload_release")
+
+    def convert_format(self, kind, d_in, d_out, n_frames, cuda_stream=None):
+        """Device form of the five other cscc.lib converters (kind 1..5, see include/livevideo.h)."""
+        import torch
+        L = capi.lib()
+        capi.check(L.lv_convert_format(
+            self._h, kind, _dev_ptr(d_in, torch.uint8, n_frames * L.lv_format_bytes(kind, self.width, self.height, 0), "d_in", self.device),
+            _dev_ptr(d_out, torch.uint8, n_frames * L.lv_format_bytes(kind, self.width, self.height, 1), "d_out", self.device),
+            n_frames, _stream_handle(cuda_stream)), "lv_convert_format")
 
     # ---- host API ------------------------------------------------------------------------------------
     def step_host(self, i420, n_streams, n_frames, bgr=None, mask_bits=None, mb_count=None, mb_map=None,

@@ -17,6 +17,11 @@ SYMBOLS = {
     "lv_version": (C.c_int, []),
     "lv_device_count": (C.c_int, []),
     "YV12_to_RGB24": (None, [_vp, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "RGB24_to_YV12": (None, [_vp, _vp, C.c_int, C.c_int]),
+    "YVU9_to_YV12": (None, [_vp, _vp, C.c_int, C.c_int]),
+    "YUY2_to_YV12": (None, [_vp, _vp, C.c_int, C.c_int]),
+    "YV12_to_YVU9": (None, [_vp, _vp, C.c_int, C.c_int]),
+    "YV12_to_YUY2": (None, [_vp, _vp, C.c_int, C.c_int]),
     "FrameDiff_MB": (None, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "lv_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "lv_destroy": (None, [_vp]),
@@ -36,6 +41,8 @@ SYMBOLS = {
     "lv_upload_async": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "lv_upload_wait": (C.c_int, [_vp, C.c_int, _vp]),
     "lv_upload_release": (C.c_int, [_vp, C.c_int, _vp]),
+    "lv_convert_format": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp]),
+    "lv_format_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "lv_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "lv_host_free": (C.c_int, [_vp]),
     "lv_step_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),

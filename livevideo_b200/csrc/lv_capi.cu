@@ -344,6 +344,21 @@ int lv_object_box(lv_ctx *c, const void *d_mask, int mask_is_bits, int x0, int x
                                                d_box4, (cudaStream_t)cuda_stream), c->launches);
 }
 
+int lv_convert_format(lv_ctx *c, int kind, const uint8_t *d_in, uint8_t *d_out, int n_frames, void *cuda_stream)
+{
+    if (!c || !d_in || !d_out || kind < 1 || kind > 5 || n_frames < 0) return LV_E_ARG;
+    if (c->g.w % 4 != 0 || c->g.h % 4 != 0) return LV_E_SIZE;
+    if (n_frames == 0) return LV_OK;
+    DeviceGuard guard(c->device);
+    return launch_result(lv::launch_format(kind, c->g.w, c->g.h, d_in, d_out, n_frames, (cudaStream_t)cuda_stream), c->launches);
+}
+
+size_t lv_format_bytes(int kind, int width, int height, int output)
+{
+    if (kind < 1 || kind > 5 || width <= 0 || height <= 0) return 0;
+    return output ? lv::format_bytes_out(kind, width, height) : lv::format_bytes_in(kind, width, height);
+}
+
 int lv_set_kernel_variant(int variant)
 {
     if (variant < 0 || variant > 2) return LV_E_ARG;
@@ -566,6 +581,34 @@ void YV12_to_RGB24(unsigned char *src0, unsigned char *src1, unsigned char *src2
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { cuda_fail(e, "D2H"); legacy_die(fn, "copy failed"); }
 }
+
+namespace {
+
+void legacy_format(const char *fn, int kind, unsigned char *in, unsigned char *out, int w, int h)
+{
+    if (!in || !out) legacy_die(fn, "NULL buffer");
+    if (w <= 0 || h <= 0) return;
+    if (w % 4 != 0 || h % 4 != 0) legacy_die(fn, "needs width % 4 == 0 and height % 4 == 0");
+    cudaStream_t st = legacy_stream(fn);
+    const size_t inb = lv::format_bytes_in(kind, w, h), outb = lv::format_bytes_out(kind, w, h);
+    uint8_t *din = t_in.get(inb), *dout = t_out.get(outb);
+    if (!din || !dout) legacy_die(fn, "device allocation failed");
+    cudaError_t e = cudaMemcpyAsync(din, in, inb, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cuda_fail(e, "H2D"); legacy_die(fn, "copy failed"); }
+    const int r = lv::launch_format(kind, w, h, din, dout, 1, st);
+    if (r < 0) { cuda_fail((cudaError_t)(-r), "launch"); legacy_die(fn, "kernel launch failed"); }
+    e = cudaMemcpyAsync(out, dout, outb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cuda_fail(e, "D2H"); legacy_die(fn, "copy failed"); }
+}
+
+}  // namespace
+
+void RGB24_to_YV12(unsigned char *in, unsigned char *out, int w, int h) { legacy_format("RGB24_to_YV12", 1, in, out, w, h); }
+void YVU9_to_YV12(unsigned char *in, unsigned char *out, int w, int h) { legacy_format("YVU9_to_YV12", 2, in, out, w, h); }
+void YUY2_to_YV12(unsigned char *in, unsigned char *out, int w, int h) { legacy_format("YUY2_to_YV12", 3, in, out, w, h); }
+void YV12_to_YVU9(unsigned char *in, unsigned char *out, int w, int h) { legacy_format("YV12_to_YVU9", 4, in, out, w, h); }
+void YV12_to_YUY2(unsigned char *in, unsigned char *out, int w, int h) { legacy_format("YV12_to_YUY2", 5, in, out, w, h); }
 
 void FrameDiff_MB(const unsigned char *cur_y, const unsigned char *ref_y, int width, int height, int tol, int mb_thresh,
                   unsigned char *mask, unsigned short *mb_count, unsigned char *mb_map)

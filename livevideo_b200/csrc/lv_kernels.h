@@ -79,6 +79,12 @@ int launch_write_bks(const Geom &g, const uint8_t *cur, const uint8_t *bkd, int 
                      uint16_t *obj_bits, cudaStream_t st);
 int launch_object_box(int w, const uint8_t *mask, bool bits, int x0, int x1, int y0, int y1, int *d_box, cudaStream_t st);
 
+// lv_formats.cu: the other five cscc.lib converters (kind 1 RGB24->YV12, 2 YVU9->YV12, 3 YUY2->YV12, 4 YV12->YVU9,
+// 5 YV12->YUY2)
+size_t format_bytes_in(int kind, int w, int h);
+size_t format_bytes_out(int kind, int w, int h);
+int launch_format(int kind, int w, int h, const uint8_t *in, uint8_t *out, int n_frames, cudaStream_t st);
+
 // any width % 4 == 0 / height % 2 == 0 (legacy geometry that is not a multiple of 16)
 int launch_convert_generic(int w, int h, const uint8_t *y, const uint8_t *u, const uint8_t *v,
                            uint8_t *bgr, cudaStream_t st);

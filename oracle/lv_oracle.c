@@ -265,6 +265,117 @@ void lvo_write_bks(const uint8_t *cur, const uint8_t *bkd, int width, int height
         out[j + voff] = lvo_is_nearly_zero((int)cur[j + voff] - (int)bkd[j + voff], tol) ? 128 : cur[j + voff];
 }
 
+/* ------------------------------------------------------------------------------------------
+ * The other five converters (object code only; see lv_oracle.h).
+ * ---------------------------------------------------------------------------------------- */
+static uint32_t r2yuv[256], g2yuv[256], b2yuv[256];
+static int rgb_tables_ready;
+
+static void init_rgb_tables(void)
+{
+    /* ctor, Convert.obj .text+0x025..0x10a: three packed tables, fields of 10 bits: Y | Cb<<10 | Cr<<20.  Every
+     * entry is __ftol(coef * i) (truncation toward zero) of the doubles in .rdata; negative contributions are
+     * kept as their low 8 bits, the field sums are taken modulo 256 by the byte stores of RGB24_to_YV12. */
+    if (rgb_tables_ready) return;
+    for (int i = 0; i < 256; i++) {
+        const uint32_t half = (uint32_t)(int)(0.5 * i);
+        r2yuv[i] = (half << 20) | (((uint32_t)(int)(-0.1687 * i) & 0xff) << 10) | (uint32_t)(int)(0.299 * i);
+        g2yuv[i] = (((uint32_t)(int)(-0.4187 * i) & 0xff) << 20) | (((uint32_t)(int)(-0.3313 * i) & 0xff) << 10) |
+                   (uint32_t)(int)(0.587 * i);
+        b2yuv[i] = (((uint32_t)(int)(-0.0813 * i) & 0xff) << 20) | (half << 10) | (uint32_t)(int)(0.114 * i);
+    }
+    rgb_tables_ready = 1;
+}
+
+void lvo_rgb24_to_yv12(const uint8_t *in, uint8_t *out, int w, int h)
+{
+    /* .text+0x1d0..0x344: 2x2 blocks, starting at the LAST DIB row (the top image row); luma for all four
+     * pixels, chroma from the top-left pixel only, XOR 0x80 */
+    init_rgb_tables();
+    const int px = w * h;
+    uint8_t *py = out, *pu = out + px, *pv = out + px + px / 4;
+    const uint8_t *row = in + 3 * w * (h - 1);
+    for (int j = h >> 1; j > 0; j--) {
+        const uint8_t *p = row;
+        for (int i = (w + 1) >> 1; i > 0; i--) {
+            const uint8_t *q = p - 3 * w;                       /* the image row below = previous DIB row */
+            uint32_t s = r2yuv[p[0]] + g2yuv[p[1]] + b2yuv[p[2]];   /* bytes are R,G,B here (+0x23e..0x25a) */
+            py[0] = (uint8_t)s;
+            *pu++ = (uint8_t)((s >> 10) ^ 0x80);
+            *pv++ = (uint8_t)((s >> 20) ^ 0x80);
+            py[w] = (uint8_t)(r2yuv[q[0]] + g2yuv[q[1]] + b2yuv[q[2]]);
+            py[1] = (uint8_t)(r2yuv[p[3]] + g2yuv[p[4]] + b2yuv[p[5]]);
+            py[w + 1] = (uint8_t)(r2yuv[q[3]] + g2yuv[q[4]] + b2yuv[q[5]]);
+            py += 2;
+            p += 6;
+        }
+        py += w;
+        row -= 6 * w;
+    }
+}
+
+void lvo_yvu9_to_yv12(const uint8_t *in, uint8_t *out, int w, int h)
+{
+    /* .text+0x740..0x8a2: every plane is read bottom-up; chroma (w/4 x h/4) is replicated 2x2 */
+    const int px = w * h, cw4 = w / 4, ch4 = h / 4, cw2 = w / 2;
+    for (int y = 0; y < h; y++) memcpy(out + (size_t)y * w, in + (size_t)(h - 1 - y) * w, (size_t)w);
+    for (int pl = 0; pl < 2; pl++) {
+        const uint8_t *src = in + px + pl * (h * cw4 / 4);
+        uint8_t *dst = out + px + pl * (h * cw2 / 2);
+        for (int y = 0; y < ch4; y++) {
+            const uint8_t *s = src + (size_t)(ch4 - 1 - y) * cw4;
+            uint8_t *d = dst + (size_t)(2 * y) * cw2;
+            for (int x = 0; x < cw4; x++) d[2 * x] = d[2 * x + 1] = s[x];
+            memcpy(d + cw2, d, (size_t)cw2);
+        }
+    }
+}
+
+void lvo_yuy2_to_yv12(const uint8_t *in, uint8_t *out, int w, int h)
+{
+    /* .text+0x8b0..0x956: Y0 U Y1 V; byte 3 feeds the FIRST chroma plane, byte 1 the second; both rows of a pair
+     * write the same chroma row, so the second (odd) row's chroma survives */
+    const int px = w * h, cw2 = w / 2;
+    uint8_t *py = out, *p1 = out + px, *p2 = out + px + px / 4;
+    for (int j = (h + 1) >> 1; j > 0; j--) {
+        for (int r = 0; r < 2; r++) {
+            for (int i = 0; i < (w + 1) >> 1; i++) {
+                *py++ = in[0]; p2[i] = in[1]; *py++ = in[2]; p1[i] = in[3];
+                in += 4;
+            }
+        }
+        p1 += cw2; p2 += cw2;
+    }
+}
+
+void lvo_yv12_to_yvu9(const uint8_t *in, uint8_t *out, int w, int h)
+{
+    /* .text+0x960..0xa39: luma copied; each chroma plane keeps every second sample of every second row */
+    const int px = w * h, cw4 = w / 4, ch4 = h / 4, cw2 = w / 2;
+    memcpy(out, in, (size_t)px);
+    const uint8_t *s = in + px;
+    uint8_t *d = out + px;
+    for (int pl = 0; pl < 2; pl++)
+        for (int y = 0; y < ch4; y++) {
+            for (int x = 0; x < cw4; x++) *d++ = s[2 * x];
+            s += 2 * cw4 + cw2;
+        }
+}
+
+void lvo_yv12_to_yuy2(const uint8_t *in, uint8_t *out, int w, int h)
+{
+    /* .text+0xa40..0xae6: inverse of YUY2_to_YV12's layout; a chroma row serves both rows of a pair */
+    const int px = w * h, cw2 = w / 2;
+    const uint8_t *py = in, *p1 = in + px, *p2 = in + px + px / 4;
+    for (int j = (h + 1) >> 1; j > 0; j--) {
+        for (int r = 0; r < 2; r++)
+            for (int i = 0; i < (w + 1) >> 1; i++) {
+                *out++ = *py++; *out++ = p2[i]; *out++ = *py++; *out++ = p1[i];
+            }
+        p1 += cw2; p2 += cw2;
+    }
+}
+
 void lvo_object_box(const uint8_t *mask, int width, int x0, int x1, int y0, int y1, int box[4])
 {
     /* image.c:4818-4838 */

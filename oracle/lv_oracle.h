@@ -62,6 +62,17 @@ void lvo_convert_diff_batch(const uint8_t *i420, uint8_t *prev_luma, int n_strea
 void lvo_write_bks(const uint8_t *cur_i420, const uint8_t *bkd_i420, int width, int height,
                    int tol, uint8_t *out_i420);
 
+/* ---- the other five converters of cscc.lib (Convert.h:25-30; never called by the application) -----------------
+ * Restated from the object code: RGB24_to_YV12 .text+0x1d0 (tables built by the ctor at .text+0x025..0x10a),
+ * YVU9_to_YV12 +0x740, YUY2_to_YV12 +0x8b0, YV12_to_YVU9 +0x960, YV12_to_YUY2 +0xa40.  "YV12" in these four
+ * packed/planar shuffles is the real YV12 (Y, then the plane fed by YUY2's V bytes, then U's); RGB24_to_YV12 writes
+ * Y, Cb, Cr.  Pinned against oracle32 modes 1..5 by tests/test_oracle.py. */
+void lvo_rgb24_to_yv12(const uint8_t *in, uint8_t *out, int w, int h);   /* in: bottom-up rows, bytes R,G,B */
+void lvo_yvu9_to_yv12(const uint8_t *in, uint8_t *out, int w, int h);    /* in is bottom-up; 2x2 replication */
+void lvo_yuy2_to_yv12(const uint8_t *in, uint8_t *out, int w, int h);    /* chroma of the odd rows wins */
+void lvo_yv12_to_yvu9(const uint8_t *in, uint8_t *out, int w, int h);    /* chroma point-sampled 2:1 both ways */
+void lvo_yv12_to_yuy2(const uint8_t *in, uint8_t *out, int w, int h);
+
 /* ---- object box from the mask (image.c:4818-4848) ----------------------------------------- */
 /* box[4] = {min_x, max_x, min_y, max_y} over mask==1 inside the window [x0..x1]x[y0..y1] (inclusive);
  * empty => {x1+1, x0-1, y1+1, y0-1} exactly as the reference initialises them. */

@@ -49,6 +49,8 @@ def lib():
                                              _u8p, _u8p, _u16p, _u8p, _u32p, C.c_int]
         L.lvo_write_bks.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, _u8p]
         L.lvo_object_box.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        for name in ("lvo_rgb24_to_yv12", "lvo_yvu9_to_yv12", "lvo_yuy2_to_yv12", "lvo_yv12_to_yvu9", "lvo_yv12_to_yuy2"):
+            getattr(L, name).argtypes = [_u8p, _u8p, C.c_int, C.c_int]
         L.lvo_lowbias32.argtypes = [C.c_uint32]
         L.lvo_lowbias32.restype = C.c_uint32
         L.lvo_gen_uniform.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _u8p]
@@ -145,6 +147,21 @@ def object_box(mask, w, x0, x1, y0, y1):
     box = (C.c_int * 4)()
     lib().lvo_object_box(_p(mask), w, x0, x1, y0, y1, box)
     return tuple(box)
+
+
+# converter name -> (oracle32 mode, input bytes per 8 px, output bytes per 8 px)
+FORMATS = {"rgb24_to_yv12": (1, 24, 12), "yvu9_to_yv12": (2, 9, 12), "yuy2_to_yv12": (3, 16, 12),
+           "yv12_to_yvu9": (4, 12, 9), "yv12_to_yuy2": (5, 12, 16)}
+
+
+def convert_format(name, data, w, h):
+    """One of the five other cscc.lib converters (C restatement)."""
+    mode, inb, outb = FORMATS[name]
+    data = np.ascontiguousarray(data, dtype=np.uint8).ravel()
+    assert data.size >= w * h // 8 * inb
+    out = np.zeros(w * h // 8 * outb, dtype=np.uint8)
+    getattr(lib(), "lvo_" + name)(_p(data), _p(out), w, h)
+    return out
 
 
 def lowbias32(x):

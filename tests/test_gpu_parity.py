@@ -109,8 +109,8 @@ def test_legacy_kats_and_layout(lv, golden, torch_cuda):
     assert [int(dst[12 + 3 * p]) for p in range(4)] == golden["chroma_kat"]["b_row1"]
     with pytest.raises(ValueError):
         csc.YV12_to_RGB24(np.zeros(6, np.uint8), np.zeros(2, np.uint8), np.zeros(2, np.uint8), np.zeros(18, np.uint8), 3, 2)
-    with pytest.raises(NotImplementedError):
-        csc.RGB24_to_YV12(None, None, 4, 2)
+    with pytest.raises(ValueError):
+        csc.RGB24_to_YV12(np.zeros(18, np.uint8), np.zeros(9, np.uint8), 3, 2)
 
 
 @pytest.mark.parametrize("w,h", [(4, 2), (8, 2), (12, 10), (20, 6), (36, 4), (100, 50), (16, 2), (32, 18), (528, 34)])
@@ -527,3 +527,39 @@ def test_upload_slots_double_buffering(lv, orc, torch_cuda):
     assert np.array_equal(np.concatenate(got_cnt), ref["mb_count"])
     assert np.array_equal(np.concatenate(got_bgr), ref["bgr"])
     ctx.close()
+
+
+@pytest.mark.parametrize("name,kind", [("rgb24_to_yv12", 1), ("yvu9_to_yv12", 2), ("yuy2_to_yv12", 3), ("yv12_to_yvu9", 4),
+                                       ("yv12_to_yuy2", 5)])
+def test_other_converters_match_object_code_semantics(lv, orc, torch_cuda, name, kind):
+    """The five Convert.h methods the application never calls: legacy host entry and batched device entry vs the
+    oracle (itself pinned to the object code on all 2^24 RGB triples / random planes)."""
+    torch = torch_cuda
+    csc = lv.ColorSpaceConversions()
+    mode, inb, outb = orc.FORMATS[name]
+    rng = np.random.default_rng(kind)
+    method = getattr(csc, {"rgb24_to_yv12": "RGB24_to_YV12", "yvu9_to_yv12": "YVU9_to_YV12", "yuy2_to_yv12": "YUY2_to_YV12",
+                           "yv12_to_yvu9": "YV12_to_YVU9", "yv12_to_yuy2": "YV12_to_YUY2"}[name])
+    for (w, h) in [(16, 8), (64, 48), (352, 288), (1920, 1080), (20, 12)]:
+        n = 3
+        data = rng.integers(0, 256, (n, w * h // 8 * inb), dtype=np.uint8)
+        want = np.stack([orc.convert_format(name, data[i], w, h) for i in range(n)])
+        out = np.zeros(w * h // 8 * outb, np.uint8)
+        method(data[0].copy(), out, w, h)
+        assert np.array_equal(out, want[0]), (name, "legacy", w, h)
+        ctx = lv.Context(w, h)
+        d_out = torch.zeros(n * w * h // 8 * outb, dtype=torch.uint8, device="cuda")
+        ctx.convert_format(kind, torch.from_numpy(data.reshape(-1)).cuda(), d_out, n)
+        assert np.array_equal(d_out.cpu().numpy(), want.reshape(-1)), (name, "device", w, h)
+        ctx.close()
+    if name == "rgb24_to_yv12":       # every (R,G,B) once as a chroma-producing pixel
+        vals = np.arange(1 << 24, dtype=np.uint32)
+        ctx = lv.Context(2048, 2048)
+        for c in (0, 7, 15):
+            v = vals[c << 20:(c + 1) << 20]
+            blk = np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], axis=-1).astype(np.uint8).reshape(1024, 1024, 3)
+            img = np.repeat(np.repeat(blk, 2, axis=0), 2, axis=1).reshape(-1)
+            d_out = torch.zeros(2048 * 2048 * 3 // 2, dtype=torch.uint8, device="cuda")
+            ctx.convert_format(1, torch.from_numpy(img).cuda(), d_out, 1)
+            assert np.array_equal(d_out.cpu().numpy(), orc.convert_format(name, img, 2048, 2048))
+        ctx.close()

@@ -208,3 +208,52 @@ def test_write_bks_and_object_box(orc):
     mask[5 * w + 7] = 1
     mask[9 * w + 3] = 1
     assert orc.object_box(mask, w, 2, 20, 1, 10) == (3, 7, 5, 9)
+
+
+# ---- the other five cscc.lib converters (Convert.h:25-30) -----------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["rgb24_to_yv12", "yvu9_to_yv12", "yuy2_to_yv12", "yv12_to_yvu9", "yv12_to_yuy2"])
+def test_other_converters_against_object_code(orc, name):
+    if not orc.have_oracle32():
+        pytest.skip("oracle32 not runnable here")
+    mode, inb, outb = orc.FORMATS[name]
+    rng = np.random.default_rng(mode)
+    for (w, h) in [(16, 8), (64, 48), (352, 288), (320, 240), (1920, 1080)]:
+        data = rng.integers(0, 256, w * h // 8 * inb, dtype=np.uint8)
+        assert np.array_equal(orc.convert_format(name, data, w, h), orc.oracle32_convert(data, w, h, mode=mode)), (name, w, h)
+
+
+def test_rgb24_to_yv12_exhaustive_against_object_code(orc):
+    """All 2^24 (R,G,B) triples, each as the top-left pixel of a 2x2 block (the one that also produces chroma)."""
+    if not orc.have_oracle32():
+        pytest.skip("oracle32 not runnable here")
+    vals = np.arange(1 << 24, dtype=np.uint32)
+    bad = 0
+    for c in range(16):
+        v = vals[c << 20:(c + 1) << 20]
+        blk = np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], axis=-1).astype(np.uint8).reshape(1024, 1024, 3)
+        img = np.zeros((2048, 2048, 3), np.uint8)
+        img[0::2, 0::2] = blk
+        img[1::2, 0::2] = blk[:, ::-1]
+        img[0::2, 1::2] = blk[::-1]
+        img[1::2, 1::2] = blk
+        data = img.reshape(-1)
+        bad += int((orc.convert_format("rgb24_to_yv12", data, 2048, 2048) != orc.oracle32_convert(data, 2048, 2048, mode=1)).sum())
+    assert bad == 0
+
+
+def test_other_converters_known_values(orc):
+    # flat colours through RGB24_to_YV12 (values recorded from the object code): bytes are R,G,B
+    for rgb, yuv in {(0, 0, 0): (0, 128, 128), (255, 0, 0): (76, 85, 255), (0, 255, 0): (149, 44, 22),
+                     (0, 0, 255): (29, 255, 108), (255, 255, 255): (254, 128, 129)}.items():
+        out = orc.convert_format("rgb24_to_yv12", np.tile(np.array(rgb, np.uint8), 16 * 8), 16, 8)
+        assert (int(out[0]), int(out[128]), int(out[160])) == yuv
+    # YUY2 -> YV12 -> YUY2 keeps luma and the odd rows' chroma
+    rng = np.random.default_rng(2)
+    w, h = 16, 8
+    yuy2 = rng.integers(0, 256, 2 * w * h, dtype=np.uint8)
+    yv12 = orc.convert_format("yuy2_to_yv12", yuy2, w, h)
+    back = orc.convert_format("yv12_to_yuy2", yv12, w, h).reshape(h, w // 2, 4)
+    src = yuy2.reshape(h, w // 2, 4)
+    assert np.array_equal(back[:, :, 0::2], src[:, :, 0::2])
+    assert np.array_equal(back[0::2, :, 1::2], src[1::2, :, 1::2]) and np.array_equal(back[1::2, :, 1::2], src[1::2, :, 1::2])
