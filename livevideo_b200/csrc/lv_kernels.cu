@@ -47,10 +47,75 @@ struct KArgs {
     uint32_t *summary;
 };
 
-__device__ __forceinline__ uint4 ld16(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
-__device__ __forceinline__ uint4 ld16_stream(const uint8_t *p) { return __ldcs(reinterpret_cast<const uint4 *>(p)); }
-__device__ __forceinline__ uint2 ld8_stream(const uint8_t *p) { return __ldcs(reinterpret_cast<const uint2 *>(p)); }
-__device__ __forceinline__ void st16_stream(uint8_t *p, const uint4 &v) { __stcs(reinterpret_cast<uint4 *>(p), v); }
+// Cache policies (A/B measured on B200, profiles/README.md).  Loads: 0 = read-only path (ld.global.nc), 1 = .cs
+// streaming, 2 = nc + L1::no_allocate, 3 = nc + L2 evict_first hint, 4 = nc + L1::no_allocate + L2 evict_first hint,
+// 5 = nc + L2 evict_last hint.  Stores: 0 = .cs, 1 = default, 4 = L1::no_allocate + L2 evict_first hint.
+#ifndef LV_LDY
+#define LV_LDY 0
+#endif
+#ifndef LV_LDP
+#define LV_LDP 0
+#endif
+#ifndef LV_LDC
+#define LV_LDC 0
+#endif
+#ifndef LV_ST_POLICY
+#define LV_ST_POLICY 0
+#endif
+
+template <int POL>
+__device__ __forceinline__ uint4 ld16_pol(const uint8_t *p)
+{
+    uint4 v;
+    if (POL == 0) return __ldg(reinterpret_cast<const uint4 *>(p));
+    if (POL == 1) return __ldcs(reinterpret_cast<const uint4 *>(p));
+    if (POL == 2) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        return v;
+    }
+    uint64_t pol;
+    if (POL == 5) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if (POL == 4)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    else
+        asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+template <int POL>
+__device__ __forceinline__ uint2 ld8_pol(const uint8_t *p)
+{
+    uint2 v;
+    if (POL == 0) return __ldg(reinterpret_cast<const uint2 *>(p));
+    if (POL == 1) return __ldcs(reinterpret_cast<const uint2 *>(p));
+    if (POL == 2) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+        return v;
+    }
+    uint64_t pol;
+    if (POL == 5) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if (POL == 4)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    else
+        asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint4 ld16(const uint8_t *p) { return ld16_pol<LV_LDY>(p); }
+__device__ __forceinline__ uint4 ld16_stream(const uint8_t *p) { return ld16_pol<LV_LDP>(p); }
+__device__ __forceinline__ uint2 ld8_stream(const uint8_t *p) { return ld8_pol<LV_LDC>(p); }
+__device__ __forceinline__ void st16_stream(uint8_t *p, const uint4 &v)
+{
+#if LV_ST_POLICY == 0
+    __stcs(reinterpret_cast<uint4 *>(p), v);
+#elif LV_ST_POLICY == 1
+    *reinterpret_cast<uint4 *>(p) = v;
+#else
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+#endif
+}
 
 // 16 pixels of one row: luma words yw[4], chroma samples c[8] -> 48 bytes
 __device__ __forceinline__ void convert_row16(const uint4 &y, const Chroma2 (&c)[8], uint8_t *dst)

@@ -14,8 +14,8 @@
 struct G { int w, h, units, nf; size_t px, frame; const uint8_t *in; uint8_t *out; };
 
 __device__ __forceinline__ uint4 ldg16(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
-__device__ __forceinline__ uint4 ldcs16(const uint8_t *p) { return __ldcs(reinterpret_cast<const uint4 *>(p)); }
-__device__ __forceinline__ uint2 ldcs8(const uint8_t *p) { return __ldcs(reinterpret_cast<const uint2 *>(p)); }
+__device__ __forceinline__ uint4 ldcs16(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }   // .cs loads cost 9 % (profiles/README.md)
+__device__ __forceinline__ uint2 ldcs8(const uint8_t *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
 __device__ __forceinline__ void stcs16(uint8_t *p, const uint4 &v) { __stcs(reinterpret_cast<uint4 *>(p), v); }
 
 template <bool kSmemStore, bool kFwdOut = false, bool kNoUV = false, bool kNoPrev = false>
