@@ -265,31 +265,45 @@ def run_ours(args):
         step()
     barrier()
     sampler = ClockSampler(local_rank)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.kernel_launches
     sampler.start()
     pending = None
+    # The timed region holds nothing but the K steps: two events on the launching stream, no per-step events (an
+    # event pair between back-to-back launches costs ~5 us per step on this kernel: 119 us vs 114 us).
+    ev0.record()
     for i in range(args.steps):
-        ev[2 * i].record()
         if world > 1:
-            # kernel + summary all-gather; the gather of step i overlaps the kernel of step i+1
+            # kernel + summary exchange; the exchange of step i overlaps the kernel of step i+1
             pending = sc.step_async(d_in, nf, out)
         else:
             ctx.convert_diff_batch(d_in, ns, nf, out)
-        ev[2 * i + 1].record()
     if pending is not None:
-        gathered = pending.result()          # the last gather is inside the timed region
+        gathered = pending.result()          # the last exchange is inside the timed region
         assert gathered.shape == (total_streams, nf, 2)
+    ev1.record()
     sampler.sample()
     barrier()
     sampler.stop()
     launches = ctx.kernel_launches - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kern_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
+    total_ms = ev0.elapsed_time(ev1)
+    # average launch duration over the timed region (one fused launch per step; the 2-word-per-frame memset of the
+    # summary and, at N > 1, the exchange are inside it, so this is an upper bound of the kernel's own time)
+    kern_ms = total_ms / args.steps
+    # the same launch bracketed by its own event pair, outside the timed region (reported beside it)
+    iso = []
+    for _ in range(min(args.steps, 50)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ctx.convert_diff_batch(d_in, ns, nf, out)
+        b.record()
+        iso.append((a, b))
+    torch.cuda.synchronize()
+    iso_ms = sorted(a.elapsed_time(b) for a, b in iso)[len(iso) // 2]
     if world > 1:
-        t = torch.tensor([total_ms, kern_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([total_ms, kern_ms, iso_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, kern_ms = float(t[0]), float(t[1])
+        total_ms, kern_ms, iso_ms = float(t[0]), float(t[1]), float(t[2])
     px_job = total_streams * nf * w * h        # pixels of one step over all ranks
     value = px_job * args.steps / (total_ms * 1e-3) / 1e6
 
@@ -357,7 +371,8 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
                      "algorithmic_bytes_per_px": BYTES_PER_PX, "px_per_launch": px_step,
-                     "kernel_us": kern_ms * 1e3, "frac_of_nominal_8TBs": achieved / 8000.0},
+                     "kernel_us": kern_ms * 1e3, "kernel_us_single_launch_events": iso_ms * 1e3,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
         "clocks": sampler.summary(),
         "gpu_launches": int(launches),
     }
