@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=0, help="host-buffer steps to time (default: min(steps, 20))")
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall-clock budget of the cpu_baseline leg")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the per-step summaries reach the other ranks (peer-memory pushes or NCCL all-gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -238,7 +240,8 @@ def run_ours(args):
     w, h, ns, nf = WORKLOADS[args.workload]
     strong = args.workload in STRONG
     total_streams = ns if strong else ns * world
-    sc = ShardedContext(w, h, total_streams, 20, 0, rank=rank, world=world, device=local_rank)
+    sc = ShardedContext(w, h, total_streams, 20, 0, rank=rank, world=world, device=local_rank,
+                        exchange="p2p" if (world > 1 and args.exchange == "p2p") else None)
     ctx = sc.ctx
     ns = sc.local_streams                      # this rank's block of streams
     n = ns * nf
@@ -255,6 +258,13 @@ def run_ours(args):
         torch.cuda.synchronize()
         mine = out["summary"][: n * 2].reshape(ns, nf, 2)
         assert torch.equal(full[sc.first_stream:sc.first_stream + ns], mine), "summary all-gather mismatch"
+        # the exchange used in the timed steps (peer-memory pushes by default) must deliver the same table as the
+        # blocking NCCL all-gather above: step twice from the same state and compare
+        sc.ctx.reset_prev_luma()
+        full = step().clone()
+        sc.ctx.reset_prev_luma()
+        got = sc.step_async(d_in, nf, out).result()
+        assert torch.equal(got, full), "summary exchange disagrees with the NCCL all-gather"
 
     def barrier():
         if world > 1:
@@ -376,6 +386,9 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "gpu_launches": int(launches),
     }
+    if world > 1:
+        line["config"]["summary_exchange"] = ("peer-memory pushes over NVLink (lv_exchange_*), no per-step collective"
+                                              if sc.exchange is not None else "NCCL all_gather_into_tensor per step")
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

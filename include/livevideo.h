@@ -214,6 +214,38 @@ LV_API int lv_get_kernel_variant(void);
 LV_API uint64_t lv_kernel_launches(const lv_ctx *ctx);   /* kernels of this library launched so far */
 LV_API int lv_device_sm_count(const lv_ctx *ctx);
 
+/* ---- peer-memory exchange of the change summaries (one process per GPU; csrc/lv_exchange.cu) ------------------------
+ * The only exchange of the sharded path: every rank wants every rank's {changed_px, changed_mbs} per
+ * (stream, frame).  Instead of a per-step library all-gather, each rank pushes its block into every peer's table with
+ * NVLink stores from one tiny kernel behind the fused kernel, followed by a sequence flag; a collect waits on local
+ * flags only.  Ranks never rendezvous; a rank blocks only when it is a whole ring (`depth` steps) ahead of a peer.
+ *
+ *   lv_exchange_create     allocates this rank's buffer (ring of `depth` tables of world x slot_words u32 + flags)
+ *   lv_exchange_handle     64-byte CUDA IPC handle of it; hand the handles of all ranks to lv_exchange_connect
+ *                          (any transport: torch.distributed, MPI, a file) or pass already-mapped pointers to
+ *                          lv_exchange_connect_ptrs (one process driving several ranks, VMM / symmetric allocations)
+ *   lv_exchange_local_block(step)  device pointer to hand to lv_convert_diff_batch as d_summary for that step: the
+ *                          fused kernel writes this rank's block in place, there is no staging copy
+ *   lv_exchange_publish(step, n_words, d_local_copy, stream)   after the fused kernel of `step` in stream order; steps
+ *                          in order; d_local_copy (optional) also receives this rank's n_words
+ *   lv_exchange_collect(step, d_table, stream)   d_table = world x slot_words u32 (row r = rank r), or NULL to retire
+ *                          the step unread; every step must be collected, in order, within `depth` steps, and the
+ *                          caller must not launch the fused kernel of step+depth before this collect has finished
+ *   lv_exchange_error      0, or which wait gave up after 4 s (1 publish / 2 collect): a wait never spins forever */
+typedef struct lv_exchange lv_exchange;
+LV_API size_t lv_exchange_bytes(int world, int depth, int slot_words);
+LV_API int lv_exchange_create(int device, int rank, int world, int depth, int slot_words, lv_exchange **out);
+LV_API void lv_exchange_destroy(lv_exchange *x);
+LV_API void *lv_exchange_buffer(lv_exchange *x);
+LV_API int lv_exchange_handle(lv_exchange *x, unsigned char *handle64);
+LV_API int lv_exchange_connect(lv_exchange *x, const unsigned char *handles);
+LV_API int lv_exchange_connect_ptrs(lv_exchange *x, void *const *peer_buffers);
+LV_API uint32_t *lv_exchange_local_block(lv_exchange *x, uint64_t step);
+LV_API int lv_exchange_publish(lv_exchange *x, uint64_t step, int n_words, uint32_t *d_local_copy, void *cuda_stream);
+LV_API int lv_exchange_collect(lv_exchange *x, uint64_t step, uint32_t *d_table, void *cuda_stream);
+LV_API int lv_exchange_error(lv_exchange *x);
+LV_API const char *lv_exchange_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,8 +194,10 @@ class Context:
         }
         return out
 
-    def convert_diff_batch(self, i420, n_streams, n_frames, out, first_stream=0, cuda_stream=None):
-        """One fused launch over n_streams*n_frames frames resident in device memory (asynchronous)."""
+    def convert_diff_batch(self, i420, n_streams, n_frames, out, first_stream=0, cuda_stream=None, summary_ptr=None):
+        """One fused launch over n_streams*n_frames frames resident in device memory (asynchronous).
+        summary_ptr: raw device address that receives the summary instead of out["summary"] (the peer exchange hands
+        out the block of its own table, livevideo_b200/shard.py)."""
         import torch
         n = n_streams * n_frames
         d = self.device
@@ -206,7 +208,7 @@ class Context:
             _dev_ptr(out.get("mask_bytes"), torch.uint8, n * self.px, "mask_bytes", d),
             _dev_ptr(out.get("mb_count"), torch.int16, n * self.mbs, "mb_count", d),
             _dev_ptr(out.get("mb_map"), torch.uint8, n * self.mbs, "mb_map", d),
-            _dev_ptr(out.get("summary"), torch.int32, n * 2, "summary", d),
+            summary_ptr if summary_ptr is not None else _dev_ptr(out.get("summary"), torch.int32, n * 2, "summary", d),
             _stream_handle(cuda_stream)), "lv_convert_diff_batch")
 
     def convert_batch(self, i420, n_frames, bgr, cuda_stream=None):

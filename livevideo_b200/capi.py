@@ -56,6 +56,18 @@ SYMBOLS = {
     "lv_gather_summaries": (C.c_int, [_vp, _vp]),
     "lv_shard_gathered": (_vp, [_vp, C.c_int]),
     "lv_shard_sync": (C.c_int, [_vp]),
+    "lv_exchange_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "lv_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "lv_exchange_destroy": (None, [_vp]),
+    "lv_exchange_buffer": (_vp, [_vp]),
+    "lv_exchange_handle": (C.c_int, [_vp, _vp]),
+    "lv_exchange_connect": (C.c_int, [_vp, _vp]),
+    "lv_exchange_connect_ptrs": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "lv_exchange_local_block": (_vp, [_vp, C.c_uint64]),
+    "lv_exchange_publish": (C.c_int, [_vp, C.c_uint64, C.c_int, _vp, _vp]),
+    "lv_exchange_collect": (C.c_int, [_vp, C.c_uint64, _vp, _vp]),
+    "lv_exchange_error": (C.c_int, [_vp]),
+    "lv_exchange_last_error": (C.c_char_p, []),
     "lv_set_kernel_variant": (C.c_int, [C.c_int]),
     "lv_get_kernel_variant": (C.c_int, []),
     "lv_kernel_launches": (C.c_uint64, [_vp]),

@@ -4,7 +4,10 @@ Camera streams are independent units: a stream's only state is its own previous 
 (lib/JM/image.c:1553-1561), and no pixel ever crosses streams.  So the path shards with NO data-path
 collective: rank g owns the contiguous block of streams [g*S/G, (g+1)*S/G) and runs the
 same fused kernel on its block.  The only exchange is the tiny per-(stream, frame) change summary
-{changed_px, changed_mbs}, all-gathered after the step (NCCL on GPUs, gloo in the CPU tests).
+{changed_px, changed_mbs}.  On GPUs every rank pushes its block into every peer's table with NVLink stores from a tiny
+kernel behind the fused kernel (PeerExchange over the C ABI's lv_exchange_*: no per-step rendezvous, no library
+collective on the step); the library all-gather (NCCL on GPUs, gloo in the CPU tests) is the blocking variant and the
+cross-check.
 """
 from typing import Optional, Tuple
 
@@ -101,13 +104,116 @@ def gather_summaries(local_summary, n_streams: int, n_frames: int, group=None):
     return torch.cat(parts, dim=0)
 
 
+class PeerExchange:
+    """lv_exchange_*: this rank's ring of summary tables, written into by every peer over NVLink.
+
+    One process per GPU: the 64-byte CUDA IPC handles travel once through torch.distributed (all_gather_object);
+    one process driving several ranks (tests): connect_local() wires the raw pointers."""
+
+    def __init__(self, device, rank, world, slot_words, depth=8):
+        import ctypes as C
+
+        from . import capi
+        self._C, self._capi = C, capi
+        self._h = C.c_void_p()
+        capi.check(capi.lib().lv_exchange_create(device, rank, world, depth, slot_words, C.byref(self._h)),
+                   "lv_exchange_create")
+        self.device, self.rank, self.world, self.slot_words, self.depth = device, rank, world, slot_words, depth
+
+    def close(self):
+        if self._h:
+            self._capi.lib().lv_exchange_destroy(self._h)
+            self._h = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def handle(self) -> bytes:
+        buf = self._C.create_string_buffer(64)
+        self._capi.check(self._capi.lib().lv_exchange_handle(self._h, buf), "lv_exchange_handle")
+        return buf.raw
+
+    def buffer_ptr(self) -> int:
+        return int(self._capi.lib().lv_exchange_buffer(self._h) or 0)
+
+    def connect(self, handles):
+        """handles[r] = rank r's handle() (bytes, 64 each)."""
+        blob = b"".join(bytes(h) for h in handles)
+        if len(blob) != 64 * self.world:
+            raise ValueError("need one 64-byte handle per rank")
+        self._capi.check(self._capi.lib().lv_exchange_connect(self._h, blob), "lv_exchange_connect")
+
+    def connect_group(self, group=None):
+        """Exchange the IPC handles over torch.distributed and map every peer's buffer."""
+        import torch.distributed as dist
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.handle(), group=group)
+        self.connect(handles)
+        dist.barrier(group=group)        # nobody publishes into a peer that has not finished mapping
+
+    @staticmethod
+    def connect_local(exchanges):
+        """All ranks live in this process: wire the raw device pointers (no IPC)."""
+        import ctypes as C
+        ptrs = (C.c_void_p * len(exchanges))(*[x.buffer_ptr() for x in exchanges])
+        for x in exchanges:
+            x._capi.check(x._capi.lib().lv_exchange_connect_ptrs(x._h, ptrs), "lv_exchange_connect_ptrs")
+
+    def local_block_ptr(self, step: int) -> int:
+        return int(self._capi.lib().lv_exchange_local_block(self._h, step) or 0)
+
+    def publish(self, step, n_words, stream, local_copy=None):
+        cp = None if local_copy is None else local_copy.data_ptr()
+        self._capi.check(self._capi.lib().lv_exchange_publish(self._h, step, n_words, cp, stream.cuda_stream),
+                         "lv_exchange_publish")
+
+    def collect(self, step, table, stream):
+        tp = None if table is None else table.data_ptr()
+        self._capi.check(self._capi.lib().lv_exchange_collect(self._h, step, tp, stream.cuda_stream),
+                         "lv_exchange_collect")
+
+    def error(self) -> int:
+        return int(self._capi.lib().lv_exchange_error(self._h))
+
+
+class PendingPeerGather:
+    """Handle of a step whose summary table arrives through the peer exchange; result() must be asked for before
+    RING further steps are issued (its table buffer is a ring slot)."""
+
+    def __init__(self, owner, step, n_frames):
+        self.owner, self.step, self.n_frames = owner, step, n_frames
+
+    def result(self):
+        import torch
+        o = self.owner
+        if o._k - self.step > o.RING:
+            raise RuntimeError("PendingPeerGather.result(): the table's ring slot has been reused")
+        o._collect_through(self.step)
+        o._side.synchronize()
+        err = o.exchange.error()
+        if err:
+            raise RuntimeError(f"peer exchange gave up waiting for a peer ({'publish' if err == 1 else 'collect'})")
+        cap = max_shard(o.total_streams, o.world)
+        tab = o._tables[self.step % o.RING][: o.world * o.exchange.slot_words].reshape(o.world, -1)
+        tab = tab[:, : cap * self.n_frames * 2].reshape(o.world, cap, self.n_frames, 2)
+        parts = [tab[r, :shard_range(o.total_streams, o.world, r)[1]] for r in range(o.world)]
+        return torch.cat(parts, dim=0)
+
+
 class ShardedContext:
     """This rank's share of `total_streams` camera streams on its own GPU."""
 
     RING = 8
 
+    LAG = 2          # peer exchange: the table of step k is collected when step k+LAG is issued (or on result())
+
     def __init__(self, width: int, height: int, total_streams: int, tol: int = 20, mb_thresh: int = 0,
-                 rank: int = 0, world: int = 1, device: Optional[int] = None):
+                 rank: int = 0, world: int = 1, device: Optional[int] = None, exchange=None):
+        """exchange: None = library all-gather (torch.distributed) in step_async; a connected PeerExchange, or the
+        string "p2p" (create one and connect it over the default process group) = peer-memory exchange."""
         from .api import Context
         self.total_streams, self.rank, self.world = total_streams, rank, world
         self.first_stream, self.local_streams = shard_range(total_streams, world, rank)
@@ -119,6 +225,69 @@ class ShardedContext:
         self._staging = [None] * self.RING
         self._gathered = [None] * self.RING
         self._k = 0
+        self.exchange = None
+        self._max_frames = None
+        if exchange == "p2p":
+            self._want_p2p = True
+        else:
+            self._want_p2p = False
+            if exchange is not None:
+                self._attach_exchange(exchange)
+
+    # ---- peer-memory exchange -------------------------------------------------------------------------------------
+    def _attach_exchange(self, x):
+        import torch
+        if x.world != self.world or x.rank != self.rank or x.depth != self.RING:
+            raise ValueError("exchange does not match this shard (world, rank, depth)")
+        self.exchange = x
+        dev = torch.device("cuda", self.device)
+        with torch.cuda.device(dev):
+            self._side = torch.cuda.Stream(device=dev)
+            self._tables = [torch.zeros(self.world * x.slot_words, dtype=torch.int32, device=dev) for _ in range(self.RING)]
+            self._ev_kernel = [torch.cuda.Event() for _ in range(self.RING)]
+            self._ev_collected = [None] * self.RING
+        self._collected = 0            # next step to collect
+
+    def _make_exchange(self, n_frames, group=None):
+        cap = max_shard(self.total_streams, self.world)
+        words = (cap * n_frames * 2 + 3) & ~3
+        x = PeerExchange(self.device, self.rank, self.world, words, depth=self.RING)
+        x.connect_group(group)
+        self._attach_exchange(x)
+
+    def _collect_through(self, step):
+        """Enqueue (side stream) the collects of every step <= `step` that has not been collected yet."""
+        import torch
+        while self._collected <= step:
+            j = self._collected
+            self.exchange.collect(j, self._tables[j % self.RING], self._side)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            self._ev_collected[j % self.RING] = ev
+            self._collected += 1
+
+    def _step_async_p2p(self, i420_local, n_frames, out):
+        import torch
+        x = self.exchange
+        n_words = self.local_streams * n_frames * 2
+        if n_words > x.slot_words:
+            raise ValueError("n_frames larger than the exchange was sized for")
+        k = self._k
+        self._k += 1
+        i = k % self.RING
+        cur = torch.cuda.current_stream(self.device)
+        if k >= self.RING:
+            # the fused kernel of step k writes this rank's block into ring slot i: step k-RING must have left it
+            self._collect_through(k - self.RING)
+            cur.wait_event(self._ev_collected[i])
+        self.ctx.convert_diff_batch(i420_local, self.local_streams, n_frames, out, summary_ptr=x.local_block_ptr(k))
+        self._ev_kernel[i].record(cur)
+        self._side.wait_event(self._ev_kernel[i])
+        local_copy = out.get("summary")
+        x.publish(k, n_words, self._side, local_copy=local_copy)
+        if k >= self.LAG:
+            self._collect_through(k - self.LAG)
+        return PendingPeerGather(self, k, n_frames)
 
     def step(self, i420_local, n_frames, out, cuda_stream=None, gather=True, group=None):
         """Fused kernel over this rank's streams, then (optionally) the summary all-gather.
@@ -135,6 +304,10 @@ class ShardedContext:
         issued RING steps ago is waited for before its buffers are reused."""
         import torch
         import torch.distributed as dist
+        if self.exchange is None and self._want_p2p and self.world > 1:
+            self._make_exchange(n_frames, group)
+        if self.exchange is not None:
+            return self._step_async_p2p(i420_local, n_frames, out)
         self.ctx.convert_diff_batch(i420_local, self.local_streams, n_frames, out)
         local = out["summary"][: self.local_streams * n_frames * 2]
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:

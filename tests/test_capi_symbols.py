@@ -76,3 +76,16 @@ def test_product_never_touches_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", os.path.join(pkg, "liblivevideo.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_exchange_argument_checks_need_no_gpu(built, lv):
+    """lv_exchange_*: sizes are pure arithmetic; creation without a device reports LV_E_NODEVICE (never a fallback)."""
+    import ctypes as C
+    L = lv.lib()
+    assert L.lv_exchange_bytes(8, 8, 128) == 4 * (8 * 8 * 128 + 8 * 8 + 8 + 4)
+    assert L.lv_exchange_bytes(0, 8, 128) == 0 and L.lv_exchange_bytes(8, 1, 128) == 0
+    h = C.c_void_p()
+    assert L.lv_exchange_create(0, 2, 2, 8, 16, C.byref(h)) == -1          # rank out of range: LV_E_ARG
+    if L.lv_device_count() == 0:
+        assert L.lv_exchange_create(0, 0, 2, 8, 16, C.byref(h)) == -3      # LV_E_NODEVICE
+        assert not h.value

@@ -563,3 +563,90 @@ def test_other_converters_match_object_code_semantics(lv, orc, torch_cuda, name,
             ctx.convert_format(1, torch.from_numpy(img).cuda(), d_out, 1)
             assert np.array_equal(d_out.cpu().numpy(), orc.convert_format(name, img, 2048, 2048))
         ctx.close()
+
+
+# ---- peer-memory exchange of the summaries (lv_exchange_*) -------------------------------------------------------
+def _local_exchanges(world, slot_words, depth=8):
+    from livevideo_b200.shard import PeerExchange
+    xs = [PeerExchange(0, r, world, slot_words, depth=depth) for r in range(world)]
+    PeerExchange.connect_local(xs)
+    return xs
+
+
+def test_peer_exchange_ring_on_one_gpu(lv, torch_cuda):
+    """G ranks in one process on one GPU (raw pointers instead of IPC): over many more steps than the ring is deep,
+    every rank's table of every step holds every rank's block, and no wait ever gives up."""
+    torch = torch_cuda
+    G, words, depth, steps = 3, 20, 4, 23           # 20 words: the scalar copy path; not a multiple of the ring
+    xs = _local_exchanges(G, words, depth)
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    tables = [[torch.zeros(G * words, dtype=torch.int32, device="cuda") for _ in range(steps)] for _ in range(G)]
+    copies = [torch.zeros(words, dtype=torch.int32, device="cuda") for _ in range(G)]
+    rng = np.random.default_rng(5)
+    blocks = rng.integers(0, 2**31 - 1, size=(steps, G, words), dtype=np.int64).astype(np.int32)
+    d_blocks = torch.from_numpy(blocks).cuda()
+    torch.cuda.synchronize()
+    lag = 2
+    for k in range(steps + lag):
+        for r in range(G):
+            with torch.cuda.stream(streams[r]):
+                if k < steps:
+                    # stand-in for the fused kernel: write this rank's block of step k in place
+                    dst = xs[r].local_block_ptr(k)
+                    holder = type("P", (), {"__cuda_array_interface__": {
+                        "shape": (words,), "typestr": "<i4", "data": (dst, False), "version": 2}})()
+                    torch.as_tensor(holder, device="cuda").copy_(d_blocks[k, r])
+                    xs[r].publish(k, words, streams[r], local_copy=copies[r])
+                if k >= lag:
+                    xs[r].collect(k - lag, tables[r][k - lag], streams[r])
+    torch.cuda.synchronize()
+    for r in range(G):
+        assert xs[r].error() == 0
+        for k in range(steps):
+            assert np.array_equal(tables[r][k].cpu().numpy().reshape(G, words), blocks[k]), (r, k)
+        assert np.array_equal(copies[r].cpu().numpy(), blocks[steps - 1, r])
+    # call-order errors are reported, not executed
+    from livevideo_b200.capi import LiveVideoError
+    with pytest.raises(LiveVideoError):
+        xs[0].publish(steps + 5, words, streams[0])          # not the next step
+    with pytest.raises(LiveVideoError):
+        xs[0].collect(steps, None, streams[0])               # not published yet
+    for x in xs:
+        x.close()
+
+
+def test_sharded_step_async_over_peer_exchange_equals_single_rank(lv, orc, torch_cuda):
+    """ShardedContext.step_async over the peer exchange (virtual ranks on one GPU): every rank ends up with the table a
+    single rank computes, step after step, across more steps than the ring is deep; out['summary'] keeps the local
+    block."""
+    torch = torch_cuda
+    from livevideo_b200.shard import PeerExchange, ShardedContext, max_shard, shard_range
+    w, h, S, T, G, steps = 64, 48, 5, 3, 2, 11
+    frames = [orc.gen_batch("camera", 7 + k, S, T, w, h) for k in range(steps)]
+    prev = np.zeros((S, w * h), np.uint8)
+    want = [orc.convert_diff_batch(f, prev, S, T, w, h, 20, 0, want_mask=False)["summary"].reshape(S, T, 2)
+            for f in frames]      # the oracle carries `prev` from step to step
+    words = (max_shard(S, G) * T * 2 + 3) & ~3
+    xs = [PeerExchange(0, r, G, words, depth=ShardedContext.RING) for r in range(G)]
+    PeerExchange.connect_local(xs)
+    scs = [ShardedContext(w, h, S, rank=r, world=G, device=0, exchange=xs[r]) for r in range(G)]
+    outs = [sc.ctx.alloc_outputs(max(sc.local_streams, 1) * T) for sc in scs]
+    fb = scs[0].ctx.frame_bytes
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    for k in range(steps):
+        handles = []
+        for r, sc in enumerate(scs):
+            first, count = shard_range(S, G, r)
+            d_in = torch.from_numpy(frames[k][first:first + count].reshape(-1).copy()).cuda()
+            with torch.cuda.stream(streams[r]):
+                handles.append(sc.step_async(d_in, T, outs[r]))
+        if k % 3 == 2 or k == steps - 1:                     # ask only now and then: the others are retired unread
+            for r, hd in enumerate(handles):
+                got = hd.result().cpu().numpy().view(np.uint32)
+                assert np.array_equal(got, want[k]), (k, r)
+                first, count = shard_range(S, G, r)
+                torch.cuda.synchronize()
+                mine = outs[r]["summary"][:count * T * 2].cpu().numpy().view(np.uint32).reshape(count, T, 2)
+                assert np.array_equal(mine, want[k][first:first + count])
+    for x in xs:
+        assert x.error() == 0
