@@ -145,6 +145,11 @@ LV_API int lv_write_bks(lv_ctx *ctx, const uint8_t *d_cur_i420, const uint8_t *d
                         uint8_t *d_out_i420, uint16_t *d_obj_bits, void *cuda_stream);
 LV_API int lv_object_box(lv_ctx *ctx, const void *d_mask, int mask_is_bits, int x0, int x1, int y0, int y1,
                          int *d_box4, void *cuda_stream);
+/* The same box for each of n_frames masks laid out back to back (the d_mask_bytes / d_mask_bits outputs of a fused
+ * launch) in ONE pass: d_boxes = 4 ints per frame.  d_boxes (and a byte mask when width % 16 == 0) must be 16-byte
+ * aligned. */
+LV_API int lv_object_box_batch(lv_ctx *ctx, const void *d_mask, int mask_is_bits, int n_frames, int x0, int x1, int y0,
+                               int y1, int *d_boxes, void *cuda_stream);
 
 /* Device-pointer form of the five converters above: kind 1 RGB24_to_YV12, 2 YVU9_to_YV12, 3 YUY2_to_YV12,
  * 4 YV12_to_YVU9, 5 YV12_to_YUY2; n_frames frames back to back (bytes per frame: lv_format_bytes). */

@@ -253,6 +253,17 @@ class Context:
             1 if mask_is_bits else 0, x0, x1, y0, y1, box.data_ptr(), _stream_handle(cuda_stream)), "lv_object_box")
         return tuple(int(v) for v in box.cpu())
 
+    def object_box_batch(self, masks, n_frames, x0, x1, y0, y1, mask_is_bits=False, cuda_stream=None):
+        """One box per frame for n_frames masks laid out back to back: int32 CUDA tensor [n_frames, 4]."""
+        import torch
+        boxes = torch.empty((n_frames, 4), dtype=torch.int32, device=torch.device("cuda", self.device))
+        need = n_frames * (self.mask_units if mask_is_bits else self.px)
+        capi.check(capi.lib().lv_object_box_batch(
+            self._h, _dev_ptr(masks, torch.int16 if mask_is_bits else torch.uint8, need, "masks", self.device),
+            1 if mask_is_bits else 0, n_frames, x0, x1, y0, y1, boxes.data_ptr(), _stream_handle(cuda_stream)),
+            "lv_object_box_batch")
+        return boxes
+
     def upload_async(self, i420_host, n_frames_total, slot):
         """Pinned host -> device slot `slot` on the context's copy stream; returns a uint8 CUDA tensor view of the slot.
         Pair with upload_wait(slot) before the consumer and upload_release(slot) after it (double buffering)."""

@@ -26,6 +26,56 @@ __device__ __forceinline__ uint32_t bks_word(uint32_t a, uint32_t b, uint32_t fi
     return (a & m) | (fill4 & ~m);
 }
 
+// 16 bytes of one frame: words i..i+3 (word index inside the frame)
+__device__ __forceinline__ uint4 bks16(const uint4 &cv, const uint4 &bv, size_t i, size_t ywords, uint32_t tol4, uint32_t ntol7,
+                                       uint32_t &g16)
+{
+    uint32_t bits[4];
+    uint4 o;
+    o.x = bks_word(cv.x, bv.x, i + 0 < ywords ? 0x10101010u : 0x80808080u, tol4, ntol7, bits[0]);
+    o.y = bks_word(cv.y, bv.y, i + 1 < ywords ? 0x10101010u : 0x80808080u, tol4, ntol7, bits[1]);
+    o.z = bks_word(cv.z, bv.z, i + 2 < ywords ? 0x10101010u : 0x80808080u, tol4, ntol7, bits[2]);
+    o.w = bks_word(cv.w, bv.w, i + 3 < ywords ? 0x10101010u : 0x80808080u, tol4, ntol7, bits[3]);
+    // 16 luma pixels = one mask unit: gather bit 7 of every byte (see diff_mask16)
+    g16 = (bits[0] * 0x00204081u >> 28) | ((bits[1] * 0x00204081u >> 28) << 4) | ((bits[2] * 0x00204081u >> 28) << 8) |
+          ((bits[3] * 0x00204081u >> 28) << 12);
+    return o;
+}
+
+// frame % 16 == 0 (any width % 8 == 0): a block owns kUnroll * 256 consecutive 16-byte words of one frame and every
+// thread keeps kUnroll loads of the current frame (HBM) and of the background (L2) in flight before it computes.
+template <int kUnroll>
+__global__ void __launch_bounds__(256) k_write_bks_v(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ bkd,
+                                                     uint8_t *__restrict__ out, uint16_t *__restrict__ obj_bits, size_t px,
+                                                     size_t frame, int tol, int units_ok)
+{
+    const uint32_t tol4 = (uint32_t)tol * 0x01010101u, ntol7 = ~tol4 & 0x7f7f7f7fu;
+    const size_t vecs = frame / 16, ywords = px / 4;
+    const int f = blockIdx.y;
+    const uint4 *c = reinterpret_cast<const uint4 *>(cur + (size_t)f * frame);
+    const uint4 *b = reinterpret_cast<const uint4 *>(bkd);
+    uint4 *o = reinterpret_cast<uint4 *>(out + (size_t)f * frame);
+    const size_t base = (size_t)blockIdx.x * (256 * kUnroll) + threadIdx.x;
+    uint4 cv[kUnroll], bv[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; k++) {
+        const size_t v = base + 256 * k;
+        if (v < vecs) {
+            cv[k] = __ldcs(c + v);
+            bv[k] = __ldg(b + v);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; k++) {
+        const size_t v = base + 256 * k;
+        if (v < vecs) {
+            uint32_t g;
+            __stcs(o + v, bks16(cv[k], bv[k], 4 * v, ywords, tol4, ntol7, g));
+            if (obj_bits && units_ok && 4 * v + 4 <= ywords) obj_bits[(size_t)f * (px / 16) + v] = (uint16_t)g;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_write_bks(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ bkd,
                                                    uint8_t *__restrict__ out, uint16_t *__restrict__ obj_bits,
                                                    size_t px, size_t frame, int n_frames, int tol, int units_ok)
@@ -36,35 +86,21 @@ __global__ void __launch_bounds__(256) k_write_bks(const uint8_t *__restrict__ c
     const uint32_t *c = reinterpret_cast<const uint32_t *>(cur + (size_t)f * frame);
     const uint32_t *b = reinterpret_cast<const uint32_t *>(bkd);
     uint32_t *o = reinterpret_cast<uint32_t *>(out + (size_t)f * frame);
-    // 4 words (16 bytes) per thread per iteration; the tail of a frame that is not a multiple of 16 bytes is
-    // handled word by word by the same loop (vector loads only where all four words exist)
+    // generic geometry (frame % 16 != 0): 4 words per thread per iteration, word by word
     for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < words; i += (size_t)gridDim.x * blockDim.x * 4) {
         uint32_t cw[4], bw[4], ow[4], bits[4];
-        const bool full = i + 4 <= words && (frame % 16 == 0);
-        if (full) {
-            const uint4 cv = __ldcs(reinterpret_cast<const uint4 *>(c + i));
-            const uint4 bv = __ldg(reinterpret_cast<const uint4 *>(b + i));
-            cw[0] = cv.x; cw[1] = cv.y; cw[2] = cv.z; cw[3] = cv.w;
-            bw[0] = bv.x; bw[1] = bv.y; bw[2] = bv.z; bw[3] = bv.w;
-        } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                cw[k] = i + k < words ? c[i + k] : 0u;
-                bw[k] = i + k < words ? b[i + k] : 0u;
-            }
+        for (int k = 0; k < 4; k++) {
+            cw[k] = i + k < words ? c[i + k] : 0u;
+            bw[k] = i + k < words ? b[i + k] : 0u;
         }
 #pragma unroll
         for (int k = 0; k < 4; k++)
             ow[k] = bks_word(cw[k], bw[k], i + k < ywords ? 0x10101010u : 0x80808080u, tol4, ntol7, bits[k]);
-        if (full) {
-            __stcs(reinterpret_cast<uint4 *>(o + i), make_uint4(ow[0], ow[1], ow[2], ow[3]));
-        } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (i + k < words) o[i + k] = ow[k];
-        }
+        for (int k = 0; k < 4; k++)
+            if (i + k < words) o[i + k] = ow[k];
         if (obj_bits && units_ok && i + 4 <= ywords) {
-            // 16 luma pixels = one mask unit: gather bit 7 of every byte (see diff_mask16)
             const uint32_t g = (bits[0] * 0x00204081u >> 28) | ((bits[1] * 0x00204081u >> 28) << 4) |
                                ((bits[2] * 0x00204081u >> 28) << 8) | ((bits[3] * 0x00204081u >> 28) << 12);
             obj_bits[(size_t)f * (px / 16) + i / 4] = (uint16_t)g;
@@ -72,27 +108,11 @@ __global__ void __launch_bounds__(256) k_write_bks(const uint8_t *__restrict__ c
     }
 }
 
-// box[0..3] = {min_x, max_x, min_y, max_y}; must be pre-initialised to {x1+1, x0-1, y1+1, y0-1}
-template <bool kBits>
-__global__ void __launch_bounds__(256) k_object_box(const uint8_t *__restrict__ mask, int w, int x0, int x1, int y0,
-                                                    int y1, int *box)
+// Block-wide min/max, then at most one atomic per bound per block -- and only when it would move the bound (the four
+// ints of 8 frames share a 128-byte line: per-warp atomics from every block serialise in one L2 slice and cost more
+// than the whole scan).  The plain pre-read can only be stale towards "less tight", so a skipped atomic is always safe.
+__device__ __forceinline__ void box_commit(int *box, int mnx, int mxx, int mny, int mxy)
 {
-    int mnx = x1 + 1, mxx = x0 - 1, mny = y1 + 1, mxy = y0 - 1;
-    const int ww = x1 - x0 + 1;
-    const long long total = (long long)ww * (y1 - y0 + 1);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int y = y0 + (int)(i / ww), x = x0 + (int)(i % ww);
-        int on;
-        if (kBits) {
-            const uint16_t u = reinterpret_cast<const uint16_t *>(mask)[(size_t)y * (w / 16) + (x >> 4)];
-            on = (u >> (x & 15)) & 1;
-        } else {
-            on = mask[(size_t)y * w + x] == 1;
-        }
-        if (on) {
-            mnx = min(mnx, x); mxx = max(mxx, x); mny = min(mny, y); mxy = max(mxy, y);
-        }
-    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
@@ -100,14 +120,167 @@ __global__ void __launch_bounds__(256) k_object_box(const uint8_t *__restrict__ 
         mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
         mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(box + 0, mnx); atomicMax(box + 1, mxx); atomicMin(box + 2, mny); atomicMax(box + 3, mxy);
+    __shared__ int4 part[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) part[warp] = make_int4(mnx, mxx, mny, mxy);
+    __syncthreads();
+    if (warp == 0) {
+        const int4 p = part[lane & 7];
+        mnx = p.x; mxx = p.y; mny = p.z; mxy = p.w;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+            mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+            mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        }
+        if (lane == 0 && mxx >= mnx) {
+            const int4 cur = __ldcg(reinterpret_cast<const int4 *>(box));
+            if (mnx < cur.x) atomicMin(box + 0, mnx);
+            if (mxx > cur.y) atomicMax(box + 1, mxx);
+            if (mny < cur.z) atomicMin(box + 2, mny);
+            if (mxy > cur.w) atomicMax(box + 3, mxy);
+        }
     }
 }
 
-__global__ void k_box_init(int *box, int x0, int x1, int y0, int y1)
+// box[0..3] = {min_x, max_x, min_y, max_y} per frame; must be pre-initialised to {x1+1, x0-1, y1+1, y0-1}.
+// Generic geometry (byte mask, w % 16 != 0): one pixel per thread iteration.
+__global__ void __launch_bounds__(256) k_object_box_scalar(const uint8_t *__restrict__ mask, int w, size_t frame_stride, int x0,
+                                                           int x1, int y0, int y1, int *boxes)
 {
-    box[0] = x1 + 1; box[1] = x0 - 1; box[2] = y1 + 1; box[3] = y0 - 1;
+    mask += (size_t)blockIdx.y * frame_stride;
+    int *box = boxes + 4 * (size_t)blockIdx.y;
+    int mnx = x1 + 1, mxx = x0 - 1, mny = y1 + 1, mxy = y0 - 1;
+    const int ww = x1 - x0 + 1;
+    const int total = ww * (y1 - y0 + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = y0 + i / ww, x = x0 + i % ww;
+        if (mask[(size_t)y * w + x] == 1) {
+            mnx = min(mnx, x); mxx = max(mxx, x); mny = min(mny, y); mxy = max(mxy, y);
+        }
+    }
+    box_commit(box, mnx, mxx, mny, mxy);
+}
+
+// bit 7 of every byte of the result = (that byte of v == 1) & clip7; exact per byte (no borrow between bytes)
+__device__ __forceinline__ uint32_t eq1_bits(uint32_t v, uint32_t clip7)
+{
+    const uint32_t y = v ^ 0x01010101u;                        // zero byte <=> mask byte == 1 (image.c tests == 1)
+    const uint32_t t = (y & 0x7f7f7f7fu) + 0x7f7f7f7fu;        // bit 7 set <=> low 7 bits non-zero
+    return ~(t | y) & clip7;                                   // one LOP3
+}
+
+// per-byte clip mask (0x80 = inside) for the 4 pixels x..x+3 against [x0, x1]
+__device__ __forceinline__ uint32_t clip7_of(int x, int x0, int x1)
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (x + k >= x0 && x + k <= x1) m |= 0x80u << (8 * k);
+    return m;
+}
+
+// w % 16 == 0.  Item = one 16-byte load: 16 pixels of the byte mask (kBits = false) or 8 units = 128 pixels of the bit
+// mask (kBits = true).  A thread keeps ONE column of items for all its rows: the per-item work is an OR into a 16-byte
+// accumulator plus "any pixel set" for the row bounds; bit positions are looked at once per column, at the end.
+// blockIdx.y = frame, blockIdx.x = a band of `rows_per_block` window rows; kBoxUnroll loads in flight per thread.
+constexpr int kBoxUnroll = 4;
+
+template <bool kBits>
+__device__ __forceinline__ uint4 box_load(const uint8_t *mask, size_t row_bytes, int w, int y, int c)
+{
+    if (!kBits) return __ldg(reinterpret_cast<const uint4 *>(mask + (size_t)y * row_bytes + (size_t)c * 16));
+    // a row of the bit mask is w/16 uint16 units = w/8 bytes: rows need not be 16-byte aligned and the last item of a
+    // row may be short
+    const uint8_t *p = mask + (size_t)y * row_bytes + (size_t)c * 16;
+    if (c * 128 + 128 <= w && (reinterpret_cast<uintptr_t>(p) & 15) == 0) return __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint16_t *pu = reinterpret_cast<const uint16_t *>(p);
+    const int nu = min(8, (w - c * 128) >> 4);
+    uint32_t wd[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if (k < nu) wd[k >> 1] |= (uint32_t)__ldg(pu + k) << (16 * (k & 1));
+    return make_uint4(wd[0], wd[1], wd[2], wd[3]);
+}
+
+template <bool kBits>
+__global__ void __launch_bounds__(256) k_object_box(const uint8_t *__restrict__ mask, int w, size_t frame_stride, int x0, int x1,
+                                                    int y0, int y1, int rows_per_block, int *boxes)
+{
+    mask += (size_t)blockIdx.y * frame_stride;
+    int *box = boxes + 4 * (size_t)blockIdx.y;
+    int mnx = x1 + 1, mxx = x0 - 1, mny = y1 + 1, mxy = y0 - 1;
+    constexpr int kPx = kBits ? 128 : 16;                 // pixels per item
+    const int c0 = x0 / kPx, cols = x1 / kPx - c0 + 1;
+    const int cpb = min(cols, 256), rpp = 256 / cpb;      // columns side by side in the block, rows per pass
+    const int j = threadIdx.x % cpb, q = threadIdx.x / cpb;
+    const size_t row_bytes = kBits ? (size_t)(w >> 3) : (size_t)w;
+    const int rb0 = y0 + blockIdx.x * rows_per_block, rb1 = min(y1 + 1, rb0 + rows_per_block);
+    if (q < rpp) {
+        for (int c = c0 + j; c < c0 + cols; c += cpb) {
+            const int xb = c * kPx;
+            uint32_t clip[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (kBits) {
+                    const int xw = xb + 32 * k;
+                    uint32_t m = 0xffffffffu;
+                    if (xw < x0) m = x0 - xw >= 32 ? 0u : m & (0xffffffffu << (x0 - xw));
+                    if (xw + 31 > x1) m = x1 < xw ? 0u : m & (0xffffffffu >> (xw + 31 - x1));
+                    clip[k] = m;
+                } else {
+                    clip[k] = clip7_of(xb + 4 * k, x0, x1);
+                }
+            }
+            uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+            for (int y = rb0 + q; y < rb1; y += kBoxUnroll * rpp) {
+                uint4 v[kBoxUnroll];
+#pragma unroll
+                for (int k = 0; k < kBoxUnroll; k++) {
+                    const int yk = y + k * rpp;
+                    v[k] = yk < rb1 ? box_load<kBits>(mask, row_bytes, w, yk, c) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < kBoxUnroll; k++) {
+                    uint4 m;
+                    if (kBits) {
+                        m = make_uint4(v[k].x & clip[0], v[k].y & clip[1], v[k].z & clip[2], v[k].w & clip[3]);
+                    } else {
+                        m = make_uint4(eq1_bits(v[k].x, clip[0]), eq1_bits(v[k].y, clip[1]), eq1_bits(v[k].z, clip[2]),
+                                       eq1_bits(v[k].w, clip[3]));
+                    }
+                    if ((m.x | m.y | m.z | m.w) != 0u) {
+                        const int yk = y + k * rpp;            // only reached for rows inside the band (padding has no set pixel)
+                        mny = min(mny, yk);
+                        mxy = max(mxy, yk);
+                    }
+                    acc.x |= m.x; acc.y |= m.y; acc.z |= m.z; acc.w |= m.w;
+                }
+            }
+            // column bounds from the accumulated item
+            const uint32_t aw[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (aw[k]) {
+                    if (kBits) {
+                        mnx = min(mnx, xb + 32 * k + __ffs(aw[k]) - 1);
+                        mxx = max(mxx, xb + 32 * k + 31 - __clz(aw[k]));
+                    } else {      // bit 7 of byte b = pixel xb + 4k + b
+                        mnx = min(mnx, xb + 4 * k + ((__ffs(aw[k]) - 1) >> 3));
+                        mxx = max(mxx, xb + 4 * k + ((31 - __clz(aw[k])) >> 3));
+                    }
+                }
+            }
+        }
+    }
+    box_commit(box, mnx, mxx, mny, mxy);
+}
+
+__global__ void k_box_init(int *boxes, int n, int x0, int x1, int y0, int y1)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n) reinterpret_cast<int4 *>(boxes)[f] = make_int4(x1 + 1, x0 - 1, y1 + 1, y0 - 1);
 }
 
 }  // namespace
@@ -119,13 +292,21 @@ int launch_write_bks(const Geom &g, const uint8_t *cur, const uint8_t *bkd, int 
     int launches = 0;
     for (int f0 = 0; f0 < n_frames; f0 += 65535) {
         const int nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
-        const size_t words = g.frame / 4;
-        unsigned bx = (unsigned)((words / 4 + 255) / 256);
-        if (bx < 1) bx = 1;
-        if (bx > 8192) bx = 8192;
-        k_write_bks<<<dim3(bx, nf), 256, 0, st>>>(cur + (size_t)f0 * g.frame, bkd, out + (size_t)f0 * g.frame,
-                                                    obj_bits ? obj_bits + (size_t)f0 * (g.px / 16) : nullptr, g.px, g.frame,
-                                                    nf, tol, g.w % 16 == 0);
+        const uint8_t *c0 = cur + (size_t)f0 * g.frame;
+        uint8_t *o0 = out + (size_t)f0 * g.frame;
+        uint16_t *b0 = obj_bits ? obj_bits + (size_t)f0 * (g.px / 16) : nullptr;
+        if (g.frame % 16 == 0 && ((reinterpret_cast<uintptr_t>(c0) | reinterpret_cast<uintptr_t>(bkd) | reinterpret_cast<uintptr_t>(o0)) & 15) == 0) {
+            constexpr int kUnroll = 4;
+            const size_t vecs = g.frame / 16;
+            const unsigned bx = (unsigned)((vecs + 256 * kUnroll - 1) / (256 * kUnroll));
+            k_write_bks_v<kUnroll><<<dim3(bx, nf), 256, 0, st>>>(c0, bkd, o0, b0, g.px, g.frame, tol, g.w % 16 == 0);
+        } else {
+            const size_t words = g.frame / 4;
+            unsigned bx = (unsigned)((words / 4 + 255) / 256);
+            if (bx < 1) bx = 1;
+            if (bx > 8192) bx = 8192;
+            k_write_bks<<<dim3(bx, nf), 256, 0, st>>>(c0, bkd, o0, b0, g.px, g.frame, nf, tol, g.w % 16 == 0);
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return -(int)e;
         launches++;
@@ -133,18 +314,44 @@ int launch_write_bks(const Geom &g, const uint8_t *cur, const uint8_t *bkd, int 
     return launches;
 }
 
-int launch_object_box(int w, const uint8_t *mask, bool bits, int x0, int x1, int y0, int y1, int *d_box, cudaStream_t st)
+int launch_object_box(int w, int h, const uint8_t *mask, bool bits, int n_frames, int x0, int x1, int y0, int y1, int *d_boxes,
+                      cudaStream_t st)
 {
-    k_box_init<<<1, 1, 0, st>>>(d_box, x0, x1, y0, y1);
-    const long long total = (long long)(x1 - x0 + 1) * (y1 - y0 + 1);
-    if (total > 0) {
-        unsigned bx = (unsigned)((total + 255) / 256);
-        if (bx > 1184) bx = 1184;
-        if (bits) k_object_box<true><<<bx, 256, 0, st>>>(mask, w, x0, x1, y0, y1, d_box);
-        else k_object_box<false><<<bx, 256, 0, st>>>(mask, w, x0, x1, y0, y1, d_box);
+    if (n_frames <= 0) return 0;
+    int launches = 0;
+    const size_t stride = bits ? (size_t)(w >> 3) * h : (size_t)w * h;
+    for (int f0 = 0; f0 < n_frames; f0 += 65535) {
+        const int nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
+        int *boxes = d_boxes + 4 * (size_t)f0;
+        const uint8_t *m = mask + (size_t)f0 * stride;
+        k_box_init<<<(nf + 255) / 256, 256, 0, st>>>(boxes, nf, x0, x1, y0, y1);
+        launches++;
+        const long long rows = (long long)y1 - y0 + 1;
+        if (x1 >= x0 && rows > 0) {
+            if (w % 16 != 0) {
+                const long long total = (long long)(x1 - x0 + 1) * rows;
+                long long bx = (total + 1023) / 1024;
+                const long long cap = (8LL * 148 * 8 + nf - 1) / nf;
+                if (bx > cap) bx = cap;
+                if (bx < 1) bx = 1;
+                k_object_box_scalar<<<dim3((unsigned)bx, nf), 256, 0, st>>>(m, w, stride, x0, x1, y0, y1, boxes);
+            } else {
+                const int per = bits ? 128 : 16;
+                const int cols = x1 / per - x0 / per + 1, cpb = cols < 256 ? cols : 256, rpp = 256 / cpb;
+                // a band = 2 passes of kBoxUnroll x rpp rows; fewer, taller bands when that would be too many blocks
+                long long rpb = 2LL * 4 * rpp;
+                const long long cap = (16LL * 148 * 8 + nf - 1) / nf;
+                if ((rows + rpb - 1) / rpb > cap) rpb = (rows + cap - 1) / cap;
+                const unsigned bx = (unsigned)((rows + rpb - 1) / rpb);
+                if (bits) k_object_box<true><<<dim3(bx, nf), 256, 0, st>>>(m, w, stride, x0, x1, y0, y1, (int)rpb, boxes);
+                else k_object_box<false><<<dim3(bx, nf), 256, 0, st>>>(m, w, stride, x0, x1, y0, y1, (int)rpb, boxes);
+            }
+            launches++;
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return -(int)e;
     }
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? (total > 0 ? 2 : 1) : -(int)e;
+    return launches;
 }
 
 }  // namespace lv

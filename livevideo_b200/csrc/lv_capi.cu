@@ -333,15 +333,24 @@ int lv_write_bks(lv_ctx *c, const uint8_t *d_cur, const uint8_t *d_bkd, int n_fr
                          c->launches);
 }
 
+int lv_object_box_batch(lv_ctx *c, const void *d_mask, int mask_is_bits, int n_frames, int x0, int x1, int y0, int y1,
+                        int *d_boxes, void *cuda_stream)
+{
+    if (!c || !d_mask || !d_boxes || n_frames < 0) return LV_E_ARG;
+    if (x0 < 0 || y0 < 0 || x1 >= c->g.w || y1 >= c->g.h) return LV_E_ARG;
+    if (mask_is_bits && c->g.w % 16 != 0) return LV_E_SIZE;
+    if ((reinterpret_cast<uintptr_t>(d_boxes) & 15) != 0) return LV_E_ARG;
+    if (!mask_is_bits && c->g.w % 16 == 0 && (reinterpret_cast<uintptr_t>(d_mask) & 15) != 0) return LV_E_ARG;
+    if (n_frames == 0) return LV_OK;
+    DeviceGuard guard(c->device);
+    return launch_result(lv::launch_object_box(c->g.w, c->g.h, static_cast<const uint8_t *>(d_mask), mask_is_bits != 0, n_frames,
+                                               x0, x1, y0, y1, d_boxes, (cudaStream_t)cuda_stream), c->launches);
+}
+
 int lv_object_box(lv_ctx *c, const void *d_mask, int mask_is_bits, int x0, int x1, int y0, int y1, int *d_box4,
                   void *cuda_stream)
 {
-    if (!c || !d_mask || !d_box4) return LV_E_ARG;
-    if (x0 < 0 || y0 < 0 || x1 >= c->g.w || y1 >= c->g.h) return LV_E_ARG;
-    if (mask_is_bits && c->g.w % 16 != 0) return LV_E_SIZE;
-    DeviceGuard guard(c->device);
-    return launch_result(lv::launch_object_box(c->g.w, static_cast<const uint8_t *>(d_mask), mask_is_bits != 0, x0, x1, y0, y1,
-                                               d_box4, (cudaStream_t)cuda_stream), c->launches);
+    return lv_object_box_batch(c, d_mask, mask_is_bits, 1, x0, x1, y0, y1, d_box4, cuda_stream);
 }
 
 int lv_convert_format(lv_ctx *c, int kind, const uint8_t *d_in, uint8_t *d_out, int n_frames, void *cuda_stream)

@@ -77,7 +77,8 @@ int launch_diff_strip(const DiffArgs &a, cudaStream_t st);
 // lv_aux.cu: background subtraction (WriteBks) and object box
 int launch_write_bks(const Geom &g, const uint8_t *cur, const uint8_t *bkd, int n_frames, int tol, uint8_t *out,
                      uint16_t *obj_bits, cudaStream_t st);
-int launch_object_box(int w, const uint8_t *mask, bool bits, int x0, int x1, int y0, int y1, int *d_box, cudaStream_t st);
+int launch_object_box(int w, int h, const uint8_t *mask, bool bits, int n_frames, int x0, int x1, int y0, int y1, int *d_boxes,
+                      cudaStream_t st);
 
 // lv_formats.cu: the other five cscc.lib converters (kind 1 RGB24->YV12, 2 YVU9->YV12, 3 YUY2->YV12, 4 YV12->YVU9,
 // 5 YV12->YUY2)

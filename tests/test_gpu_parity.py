@@ -354,6 +354,34 @@ def test_object_box_matches_reference_scan(lv, orc, torch_cuda):
     ctx.close()
 
 
+@pytest.mark.parametrize("w,h", [(352, 288), (1920, 1080), (64, 48), (20, 12), (4096, 24)])
+def test_object_box_batch_matches_reference_scan(lv, orc, torch_cuda, w, h):
+    """One pass over a batch of masks (the vector kernels when w % 16 == 0, 128-pixel items for the bit mask with ragged
+    row tails at 352 and 1920 -> w/16 not a multiple of 8) against the reference's per-picture scan; values other than
+    1 in the byte mask are not 'on' (image.c tests == 1)."""
+    torch = torch_cuda
+    rng = np.random.default_rng(w + h)
+    n = 5
+    ctx = lv.Context(w, h)
+    dens = [0.0, 0.0002, 0.01, 0.3, 1.0]
+    masks = np.stack([(rng.random(w * h) < d).astype(np.uint8) for d in dens])
+    noisy = masks.copy()
+    noisy[2][masks[2] == 0] = rng.choice(np.array([0, 2, 255], np.uint8), size=int((masks[2] == 0).sum()))
+    windows = [(0, w - 1, 0, h - 1), (w // 3, w // 3, h // 2, h // 2), (1, w - 2, 1, h - 2), (w // 2 - 3, w // 2 + 9, 0, h - 1),
+               (w - 5, w - 1, h - 3, h - 1), (0, min(w - 1, 130), 2, min(h - 1, 9))]
+    d_bytes = torch.from_numpy(noisy.reshape(-1)).cuda()
+    for (x0, x1, y0, y1) in windows:
+        want = np.array([orc.object_box(masks[i], w, x0, x1, y0, y1) for i in range(n)], np.int32)
+        got = ctx.object_box_batch(d_bytes, n, x0, x1, y0, y1).cpu().numpy()
+        assert np.array_equal(got, want), ("bytes", w, h, x0, x1, y0, y1)
+        if w % 16 == 0:
+            bits = np.concatenate([orc.pack_mask16(masks[i], w, h) for i in range(n)])
+            d_bits = torch.from_numpy(bits.view(np.int16)).cuda()
+            got = ctx.object_box_batch(d_bits, n, x0, x1, y0, y1, mask_is_bits=True).cpu().numpy()
+            assert np.array_equal(got, want), ("bits", w, h, x0, x1, y0, y1)
+    ctx.close()
+
+
 # ---- every kernel variant computes the same bytes --------------------------------------------------------------
 
 @pytest.mark.parametrize("variant", ["tile", "tma", "strip"])
@@ -555,7 +583,7 @@ def test_other_converters_match_object_code_semantics(lv, orc, torch_cuda, name,
     if name == "rgb24_to_yv12":       # every (R,G,B) once as a chroma-producing pixel
         vals = np.arange(1 << 24, dtype=np.uint32)
         ctx = lv.Context(2048, 2048)
-        for c in (0, 7, 15):
+        for c in range(16):
             v = vals[c << 20:(c + 1) << 20]
             blk = np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], axis=-1).astype(np.uint8).reshape(1024, 1024, 3)
             img = np.repeat(np.repeat(blk, 2, axis=0), 2, axis=1).reshape(-1)
