@@ -174,6 +174,11 @@ LV_API int lv_upload_wait(lv_ctx *ctx, int slot, void *cuda_stream);
 LV_API int lv_upload_release(lv_ctx *ctx, int slot, void *cuda_stream);   /* call after enqueuing the slot's consumer */
 LV_API int lv_host_alloc(void **p, size_t bytes);
 LV_API int lv_host_free(void *p);
+/* Pin buffers the application already owns (the reference mallocs its planes and RGB buffer once and reuses them for
+ * every picture, MainDlg.cpp:39-51): every entry that takes host pointers -- the legacy ones included -- then copies
+ * by DMA instead of through the driver's pageable staging.  Keep the range allocated until lv_host_unregister. */
+LV_API int lv_host_register(void *p, size_t bytes);
+LV_API int lv_host_unregister(void *p);
 LV_API int lv_step_host(lv_ctx *ctx, const uint8_t *h_i420, int first_stream, int n_streams, int n_frames,
                         uint8_t *h_bgr, uint16_t *h_mask_bits, uint16_t *h_mb_count, uint8_t *h_mb_map,
                         uint32_t *h_summary);

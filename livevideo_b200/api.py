@@ -338,6 +338,15 @@ def pinned(nbytes, dtype=np.uint8):
     return PinnedArray(nbytes, dtype)
 
 
+def host_register(a):
+    """Pin a numpy array the caller already owns (lv_host_register); keep it alive until host_unregister(a)."""
+    capi.check(capi.lib().lv_host_register(a.ctypes.data, a.nbytes), "lv_host_register")
+
+
+def host_unregister(a):
+    capi.check(capi.lib().lv_host_unregister(a.ctypes.data), "lv_host_unregister")
+
+
 KERNEL_VARIANTS = {"tile": 0, "tma": 1, "strip": 2}
 
 

@@ -46,6 +46,8 @@ SYMBOLS = {
     "lv_format_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "lv_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "lv_host_free": (C.c_int, [_vp]),
+    "lv_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "lv_host_unregister": (C.c_int, [_vp]),
     "lv_step_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lv_shard_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "lv_shard_destroy": (None, [_vp]),

@@ -441,6 +441,23 @@ int lv_host_free(void *p)
     return LV_OK;
 }
 
+// Pin memory the application already owns (the reference's dialogs malloc their planes and the RGB buffer once,
+// MainDlg.cpp:39-51, and reuse them for every picture): the legacy entries and lv_step_host then DMA straight from / to
+// it instead of going through the driver's pageable staging.  The range must stay allocated until lv_host_unregister.
+int lv_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes) return LV_E_ARG;
+    LV_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return LV_OK;
+}
+
+int lv_host_unregister(void *p)
+{
+    if (!p) return LV_OK;
+    LV_CUDA(cudaHostUnregister(p));
+    return LV_OK;
+}
+
 // Host step.  The batch is cut along the frame axis into chunks (all streams, a few frames each):
 // chunk k's previous luma is chunk k-1's last frame, which is exactly what the carried state holds
 // after chunk k-1's kernel, so chunking does not change any result.

@@ -678,3 +678,50 @@ def test_sharded_step_async_over_peer_exchange_equals_single_rank(lv, orc, torch
                 assert np.array_equal(mine, want[k][first:first + count])
     for x in xs:
         assert x.error() == 0
+
+
+# ---- the drop-in entries as an application calls them -------------------------------------------------------------
+def test_legacy_entries_from_several_threads_and_registered_buffers(lv, orc, torch_cuda):
+    """YV12_to_RGB24 / FrameDiff_MB are thread-safe (a context per thread) and give the same bytes whether the
+    caller's buffers are pageable or pinned in place with lv_host_register (the reference mallocs its planes once,
+    MainDlg.cpp:39-51)."""
+    import mmap
+    import threading
+    w, h = 1280, 720
+    px = w * h
+    csc = lv.ColorSpaceConversions()
+    frames = orc.gen_batch("camera", 11, 4, 2, w, h)          # 4 threads x (reference frame, current frame)
+    prev = np.zeros((4, px), np.uint8)
+    ref = orc.convert_diff_batch(frames, prev, 4, 2, w, h, 20, 0)
+    errors = []
+
+    def worker(i, register):
+        try:
+            bufs = [np.frombuffer(mmap.mmap(-1, n), dtype=np.uint8, count=n) for n in (px, px // 4, px // 4, 3 * px, px, px)]
+            y, u, v, dst, ry, mask = bufs
+            cur = frames[i, 1]
+            y[:], u[:], v[:], ry[:] = cur[:px], cur[px:px + px // 4], cur[px + px // 4:], frames[i, 0, :px]
+            if register:
+                for a in bufs:
+                    lv.host_register(a)
+            for _ in range(3):
+                dst[:] = 0
+                csc.YV12_to_RGB24(y, u, v, dst, w, h)
+                m, cnt, mp = lv.FrameDiff_MB(y, ry, w, h, 20, 0, mask=mask)
+                f = i * 2 + 1
+                assert np.array_equal(dst, ref["bgr"][f * 3 * px:(f + 1) * 3 * px])
+                assert np.array_equal(m, ref["mask"][f * px:(f + 1) * px])
+                mbs = cnt.size
+                assert np.array_equal(cnt, ref["mb_count"][f * mbs:(f + 1) * mbs])
+                assert np.array_equal(mp, ref["mb_map"][f * mbs:(f + 1) * mbs])
+            if register:
+                for a in bufs:
+                    lv.host_unregister(a)
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, register, repr(e)))
+
+    for register in (False, True):
+        ths = [threading.Thread(target=worker, args=(i, register)) for i in range(4)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+    assert not errors, errors
