@@ -254,6 +254,16 @@ LV_API uint32_t *lv_exchange_local_block(lv_exchange *x, uint64_t step);
 LV_API int lv_exchange_publish(lv_exchange *x, uint64_t step, int n_words, uint32_t *d_local_copy, void *cuda_stream);
 LV_API int lv_exchange_collect(lv_exchange *x, uint64_t step, uint32_t *d_table, void *cuda_stream);
 LV_API int lv_exchange_error(lv_exchange *x);
+/* The whole sharded step in one call: lv_convert_diff_batch with its summary written straight into this rank's block of
+ * the ring, the push to every peer and the collect of an earlier step on the exchange's own side stream.  d_summary
+ * (optional) still receives this rank's block.  *step = the step's number; lv_exchange_result(step) blocks the host
+ * until every rank's block of that step has arrived and returns the table (world rows of slot_words u32, device memory
+ * owned by the exchange, valid until `depth` further steps have been issued).  Do not mix with manual publish/collect. */
+LV_API int lv_exchange_step(lv_exchange *x, lv_ctx *ctx, const uint8_t *d_i420, int first_stream, int n_streams,
+                            int n_frames, uint8_t *d_bgr, uint16_t *d_mask_bits, uint8_t *d_mask_bytes,
+                            uint16_t *d_mb_count, uint8_t *d_mb_map, uint32_t *d_summary, void *cuda_stream,
+                            uint64_t *step);
+LV_API int lv_exchange_result(lv_exchange *x, uint64_t step, const uint32_t **d_table);
 LV_API const char *lv_exchange_last_error(void);
 
 #ifdef __cplusplus

@@ -70,6 +70,9 @@ SYMBOLS = {
     "lv_exchange_publish": (C.c_int, [_vp, C.c_uint64, C.c_int, _vp, _vp]),
     "lv_exchange_collect": (C.c_int, [_vp, C.c_uint64, _vp, _vp]),
     "lv_exchange_error": (C.c_int, [_vp]),
+    "lv_exchange_step": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   C.POINTER(C.c_uint64)]),
+    "lv_exchange_result": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "lv_exchange_last_error": (C.c_char_p, []),
     "lv_set_kernel_variant": (C.c_int, [C.c_int]),
     "lv_get_kernel_variant": (C.c_int, []),

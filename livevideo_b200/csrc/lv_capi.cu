@@ -572,15 +572,37 @@ struct LegacyBuf {
 };
 thread_local LegacyBuf t_in, t_out;
 thread_local cudaStream_t t_stream = nullptr;
+thread_local int t_device = -1;       // the device this thread's stream and scratch buffers live on
 
-cudaStream_t legacy_stream(const char *fn)
-{
-    if (!t_stream && cudaStreamCreateWithFlags(&t_stream, cudaStreamNonBlocking) != cudaSuccess) {
-        cuda_fail(cudaGetLastError(), "cudaStreamCreate");
-        legacy_die(fn, "no usable CUDA device");
+// The per-thread stream and scratch buffers are created on the device that is current at the thread's first legacy
+// call and stay there: later calls switch to that device for their duration (the application, or another library in
+// the process, may have made a different device current in between).
+struct LegacyScope {
+    DeviceGuard *guard = nullptr;
+    cudaStream_t st = nullptr;
+    explicit LegacyScope(const char *fn)
+    {
+        if (t_device < 0) {
+            int d = 0;
+            if (cudaGetDevice(&d) != cudaSuccess) {
+                cuda_fail(cudaGetLastError(), "cudaGetDevice");
+                legacy_die(fn, "no usable CUDA device");
+            }
+            t_device = d;
+        }
+        guard = new DeviceGuard(t_device);
+        if (!guard->ok) {
+            cuda_fail(cudaGetLastError(), "cudaSetDevice");
+            legacy_die(fn, "no usable CUDA device");
+        }
+        if (!t_stream && cudaStreamCreateWithFlags(&t_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cuda_fail(cudaGetLastError(), "cudaStreamCreate");
+            legacy_die(fn, "no usable CUDA device");
+        }
+        st = t_stream;
     }
-    return t_stream;
-}
+    ~LegacyScope() { delete guard; }
+};
 
 }  // namespace
 
@@ -591,7 +613,8 @@ void YV12_to_RGB24(unsigned char *src0, unsigned char *src1, unsigned char *src2
     if (!src0 || !src1 || !src2 || !dst_ori) legacy_die(fn, "NULL plane");
     if (width <= 0 || height <= 0) return;   // the original's loops run zero times
     if (width % 4 != 0 || height % 2 != 0) legacy_die(fn, "needs width % 4 == 0 and height % 2 == 0 (the original overruns)");
-    cudaStream_t st = legacy_stream(fn);
+    LegacyScope scope(fn);
+    cudaStream_t st = scope.st;
     const size_t px = (size_t)width * height;
     uint8_t *din = t_in.get(px + px / 2), *dout = t_out.get(3 * px);
     if (!din || !dout) legacy_die(fn, "device allocation failed");
@@ -615,7 +638,8 @@ void legacy_format(const char *fn, int kind, unsigned char *in, unsigned char *o
     if (!in || !out) legacy_die(fn, "NULL buffer");
     if (w <= 0 || h <= 0) return;
     if (w % 4 != 0 || h % 4 != 0) legacy_die(fn, "needs width % 4 == 0 and height % 4 == 0");
-    cudaStream_t st = legacy_stream(fn);
+    LegacyScope scope(fn);
+    cudaStream_t st = scope.st;
     const size_t inb = lv::format_bytes_in(kind, w, h), outb = lv::format_bytes_out(kind, w, h);
     uint8_t *din = t_in.get(inb), *dout = t_out.get(outb);
     if (!din || !dout) legacy_die(fn, "device allocation failed");
@@ -644,7 +668,8 @@ void FrameDiff_MB(const unsigned char *cur_y, const unsigned char *ref_y, int wi
     if (width <= 0 || height <= 0) return;
     if (tol < 0) tol = -1;          // IsNearlyZero(a, tol<0) is never true except ... nothing: every pixel changed
     if (tol > 255) tol = 255;
-    cudaStream_t st = legacy_stream(fn);
+    LegacyScope scope(fn);
+    cudaStream_t st = scope.st;
     const size_t px = (size_t)width * height;
     const int mb_w = (width + 15) / 16, mb_h = (height + 15) / 16;
     const size_t mbs = (size_t)mb_w * mb_h;

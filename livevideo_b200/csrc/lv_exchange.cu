@@ -165,7 +165,12 @@ struct lv_exchange {
     bool opened[kMaxWorld] = {};     // peers.p[r] came from cudaIpcOpenMemHandle
     bool connected = false;
     uint64_t published = 0, collected = 0;
-    uint32_t *h_err = nullptr;
+    // lv_exchange_step: the side stream the pushes / collects run on, ring of events and of collected tables
+    cudaStream_t side = nullptr;
+    cudaEvent_t *ev_kernel = nullptr, *ev_collected = nullptr;   // depth each
+    uint32_t *tables = nullptr;                                  // depth x world x slot_words
+    uint64_t steps = 0;                                          // next step of lv_exchange_step
+    int lag = 2;                                                 // step k's table is collected when step k+lag is issued
 };
 
 namespace {
@@ -233,6 +238,15 @@ void lv_exchange_destroy(lv_exchange *x)
     cudaDeviceSynchronize();
     for (int r = 0; r < x->world; r++)
         if (x->opened[r]) cudaIpcCloseMemHandle(x->peers.p[r]);
+    if (x->ev_kernel)
+        for (int i = 0; i < x->L.depth; i++) {
+            if (x->ev_kernel[i]) cudaEventDestroy(x->ev_kernel[i]);
+            if (x->ev_collected[i]) cudaEventDestroy(x->ev_collected[i]);
+        }
+    delete[] x->ev_kernel;
+    delete[] x->ev_collected;
+    if (x->side) cudaStreamDestroy(x->side);
+    cudaFree(x->tables);
     cudaFree(x->local);
     delete x;
 }
@@ -327,6 +341,98 @@ int lv_exchange_error(lv_exchange *x)
     uint32_t v = 0;
     X_CUDA(cudaMemcpy(&v, x->local + x->L.err_off(), sizeof v, cudaMemcpyDeviceToHost));
     return (int)v;
+}
+
+// ---- the whole sharded step in one call ------------------------------------------------------------------------------
+// lv_exchange_step = lv_convert_diff_batch writing its summary straight into this rank's block of the ring, then (on the
+// exchange's own side stream, behind an event) the push to every peer and the collect of step k - lag.  The caller's
+// stream only ever waits for the collect of step k - depth, which finished long ago unless a peer is a ring behind.
+namespace {
+int ensure_step_state(lv_exchange *x)
+{
+    if (x->side) return LV_OK;
+    const int d = x->L.depth;
+    X_CUDA(cudaStreamCreateWithFlags(&x->side, cudaStreamNonBlocking));
+    x->ev_kernel = new (std::nothrow) cudaEvent_t[d]();
+    x->ev_collected = new (std::nothrow) cudaEvent_t[d]();
+    if (!x->ev_kernel || !x->ev_collected) return LV_E_NOMEM;
+    for (int i = 0; i < d; i++) {
+        X_CUDA(cudaEventCreateWithFlags(&x->ev_kernel[i], cudaEventDisableTiming));
+        X_CUDA(cudaEventCreateWithFlags(&x->ev_collected[i], cudaEventDisableTiming));
+    }
+    X_CUDA(cudaMalloc(&x->tables, sizeof(uint32_t) * (size_t)d * x->world * x->L.slot_words));
+    return LV_OK;
+}
+
+int collect_through(lv_exchange *x, uint64_t step)
+{
+    while (x->collected <= step) {
+        const uint64_t j = x->collected;
+        const int slot = (int)(j % (uint64_t)x->L.depth);
+        int rc = lv_exchange_collect(x, j, x->tables + (size_t)slot * x->world * x->L.slot_words, x->side);
+        if (rc != LV_OK) return rc;
+        X_CUDA(cudaEventRecord(x->ev_collected[slot], x->side));
+    }
+    return LV_OK;
+}
+}  // namespace
+
+int lv_exchange_step(lv_exchange *x, lv_ctx *ctx, const uint8_t *d_i420, int first_stream, int n_streams, int n_frames,
+                     uint8_t *d_bgr, uint16_t *d_mask_bits, uint8_t *d_mask_bytes, uint16_t *d_mb_count, uint8_t *d_mb_map,
+                     uint32_t *d_summary, void *cuda_stream, uint64_t *step_out)
+{
+    if (!x || !ctx || n_streams < 0 || n_frames < 0) return LV_E_ARG;
+    const long long n_words = 2LL * n_streams * n_frames;
+    if (n_words > x->L.slot_words) return LV_E_ARG;
+    if (!x->connected || x->steps != x->published) return LV_E_STATE;    // not mixed with manual publish calls
+    DevGuard g(x->device);
+    int rc = ensure_step_state(x);
+    if (rc != LV_OK) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const uint64_t k = x->steps;
+    const int slot = (int)(k % (uint64_t)x->L.depth);
+    if (k >= (uint64_t)x->L.depth) {
+        // the fused kernel of step k overwrites this rank's block in ring slot `slot`: step k-depth must have left it
+        rc = collect_through(x, k - (uint64_t)x->L.depth);
+        if (rc != LV_OK) return rc;
+        X_CUDA(cudaStreamWaitEvent(st, x->ev_collected[slot], 0));
+    }
+    uint32_t *block = lv_exchange_local_block(x, k);
+    if (n_words > 0) {
+        rc = lv_convert_diff_batch(ctx, d_i420, first_stream, n_streams, n_frames, d_bgr, d_mask_bits, d_mask_bytes, d_mb_count,
+                                   d_mb_map, block, cuda_stream);
+        if (rc != LV_OK) return rc;
+    }
+    X_CUDA(cudaEventRecord(x->ev_kernel[slot], st));
+    X_CUDA(cudaStreamWaitEvent(x->side, x->ev_kernel[slot], 0));
+    rc = lv_exchange_publish(x, k, (int)n_words, d_summary, x->side);
+    if (rc != LV_OK) return rc;
+    x->steps++;
+    if (k >= (uint64_t)x->lag) {
+        rc = collect_through(x, k - (uint64_t)x->lag);
+        if (rc != LV_OK) return rc;
+    }
+    if (step_out) *step_out = k;
+    return LV_OK;
+}
+
+/* Table of `step` (world rows of slot_words u32, device memory owned by the exchange, valid until `depth` further steps
+ * have been issued).  Blocks the host until every rank's block of that step has arrived. */
+int lv_exchange_result(lv_exchange *x, uint64_t step, const uint32_t **d_table)
+{
+    if (!x || !d_table) return LV_E_ARG;
+    if (!x->side || step >= x->steps || x->steps - step > (uint64_t)x->L.depth) return LV_E_STATE;
+    DevGuard g(x->device);
+    int rc = collect_through(x, step);
+    if (rc != LV_OK) return rc;
+    X_CUDA(cudaStreamSynchronize(x->side));
+    const int err = lv_exchange_error(x);
+    if (err != 0) {
+        snprintf(x_err, sizeof x_err, "peer exchange gave up waiting for a peer (%s)", err == 1 ? "publish" : "collect");
+        return LV_E_STATE;
+    }
+    *d_table = x->tables + (size_t)(step % (uint64_t)x->L.depth) * x->world * x->L.slot_words;
+    return LV_OK;
 }
 
 }  // extern "C"

@@ -191,10 +191,13 @@ int lv_shard_step(lv_shard *s, const uint8_t *const *d_i420, int n_frames, uint8
                   uint16_t *const *d_mb_count, uint8_t *const *d_mb_map)
 {
     if (!s || !d_i420 || n_frames < 1) return LV_E_ARG;
-    int rc = ensure_summary_buffers(s, n_frames);
-    if (rc != LV_OK) return rc;
     int prev = 0;
     cudaGetDevice(&prev);
+    int rc = ensure_summary_buffers(s, n_frames);      // switches devices: restore the caller's below
+    if (rc != LV_OK) {
+        cudaSetDevice(prev);
+        return rc;
+    }
     for (int i = 0; i < s->n_dev && rc == LV_OK; i++) {
         Rank &k = s->r[i];
         if (k.count == 0) continue;

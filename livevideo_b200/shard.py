@@ -178,6 +178,33 @@ class PeerExchange:
     def error(self) -> int:
         return int(self._capi.lib().lv_exchange_error(self._h))
 
+    def step(self, ctx, i420, first_stream, n_streams, n_frames, out, stream) -> int:
+        """lv_exchange_step: fused kernel + push + lagged collect in one C call; returns the step number."""
+        import torch
+
+        from .api import _dev_ptr
+        n, d = n_streams * n_frames, ctx.device
+        k = self._C.c_uint64()
+        self._capi.check(self._capi.lib().lv_exchange_step(
+            self._h, ctx._h, _dev_ptr(i420, torch.uint8, n * ctx.frame_bytes, "i420", d), first_stream, n_streams, n_frames,
+            _dev_ptr(out.get("bgr"), torch.uint8, n * ctx.bgr_bytes, "bgr", d),
+            _dev_ptr(out.get("mask_bits"), torch.int16, n * ctx.mask_units, "mask_bits", d),
+            _dev_ptr(out.get("mask_bytes"), torch.uint8, n * ctx.px, "mask_bytes", d),
+            _dev_ptr(out.get("mb_count"), torch.int16, n * ctx.mbs, "mb_count", d),
+            _dev_ptr(out.get("mb_map"), torch.uint8, n * ctx.mbs, "mb_map", d),
+            _dev_ptr(out.get("summary"), torch.int32, n * 2, "summary", d),
+            stream.cuda_stream, self._C.byref(k)), "lv_exchange_step")
+        return k.value
+
+    def result(self, step):
+        """int32 CUDA tensor [world, slot_words]: the table of `step` (a copy; blocks until every block has arrived)."""
+        from .api import _DevView
+        p = self._C.c_void_p()
+        self._capi.check(self._capi.lib().lv_exchange_result(self._h, step, self._C.byref(p)), "lv_exchange_result")
+        nbytes = 4 * self.world * self.slot_words
+        import torch
+        return _DevView(p.value, nbytes, self.device).tensor().view(torch.int32).reshape(self.world, self.slot_words).clone()
+
 
 class PendingPeerGather:
     """Handle of a step whose summary table arrives through the peer exchange; result() must be asked for before
@@ -189,15 +216,8 @@ class PendingPeerGather:
     def result(self):
         import torch
         o = self.owner
-        if o._k - self.step > o.RING:
-            raise RuntimeError("PendingPeerGather.result(): the table's ring slot has been reused")
-        o._collect_through(self.step)
-        o._side.synchronize()
-        err = o.exchange.error()
-        if err:
-            raise RuntimeError(f"peer exchange gave up waiting for a peer ({'publish' if err == 1 else 'collect'})")
+        tab = o.exchange.result(self.step)
         cap = max_shard(o.total_streams, o.world)
-        tab = o._tables[self.step % o.RING][: o.world * o.exchange.slot_words].reshape(o.world, -1)
         tab = tab[:, : cap * self.n_frames * 2].reshape(o.world, cap, self.n_frames, 2)
         parts = [tab[r, :shard_range(o.total_streams, o.world, r)[1]] for r in range(o.world)]
         return torch.cat(parts, dim=0)
@@ -207,8 +227,6 @@ class ShardedContext:
     """This rank's share of `total_streams` camera streams on its own GPU."""
 
     RING = 8
-
-    LAG = 2          # peer exchange: the table of step k is collected when step k+LAG is issued (or on result())
 
     def __init__(self, width: int, height: int, total_streams: int, tol: int = 20, mb_thresh: int = 0,
                  rank: int = 0, world: int = 1, device: Optional[int] = None, exchange=None):
@@ -236,17 +254,9 @@ class ShardedContext:
 
     # ---- peer-memory exchange -------------------------------------------------------------------------------------
     def _attach_exchange(self, x):
-        import torch
         if x.world != self.world or x.rank != self.rank or x.depth != self.RING:
             raise ValueError("exchange does not match this shard (world, rank, depth)")
         self.exchange = x
-        dev = torch.device("cuda", self.device)
-        with torch.cuda.device(dev):
-            self._side = torch.cuda.Stream(device=dev)
-            self._tables = [torch.zeros(self.world * x.slot_words, dtype=torch.int32, device=dev) for _ in range(self.RING)]
-            self._ev_kernel = [torch.cuda.Event() for _ in range(self.RING)]
-            self._ev_collected = [None] * self.RING
-        self._collected = 0            # next step to collect
 
     def _make_exchange(self, n_frames, group=None):
         cap = max_shard(self.total_streams, self.world)
@@ -255,38 +265,11 @@ class ShardedContext:
         x.connect_group(group)
         self._attach_exchange(x)
 
-    def _collect_through(self, step):
-        """Enqueue (side stream) the collects of every step <= `step` that has not been collected yet."""
-        import torch
-        while self._collected <= step:
-            j = self._collected
-            self.exchange.collect(j, self._tables[j % self.RING], self._side)
-            ev = torch.cuda.Event()
-            ev.record(self._side)
-            self._ev_collected[j % self.RING] = ev
-            self._collected += 1
-
     def _step_async_p2p(self, i420_local, n_frames, out):
         import torch
-        x = self.exchange
-        n_words = self.local_streams * n_frames * 2
-        if n_words > x.slot_words:
-            raise ValueError("n_frames larger than the exchange was sized for")
-        k = self._k
-        self._k += 1
-        i = k % self.RING
-        cur = torch.cuda.current_stream(self.device)
-        if k >= self.RING:
-            # the fused kernel of step k writes this rank's block into ring slot i: step k-RING must have left it
-            self._collect_through(k - self.RING)
-            cur.wait_event(self._ev_collected[i])
-        self.ctx.convert_diff_batch(i420_local, self.local_streams, n_frames, out, summary_ptr=x.local_block_ptr(k))
-        self._ev_kernel[i].record(cur)
-        self._side.wait_event(self._ev_kernel[i])
-        local_copy = out.get("summary")
-        x.publish(k, n_words, self._side, local_copy=local_copy)
-        if k >= self.LAG:
-            self._collect_through(k - self.LAG)
+        k = self.exchange.step(self.ctx, i420_local, 0, self.local_streams, n_frames, out,
+                               torch.cuda.current_stream(self.device))
+        self._k = k + 1
         return PendingPeerGather(self, k, n_frames)
 
     def step(self, i420_local, n_frames, out, cuda_stream=None, gather=True, group=None):

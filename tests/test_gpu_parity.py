@@ -18,6 +18,18 @@ def torch_cuda():
     return torch
 
 
+@pytest.fixture(autouse=True)
+def _device_unchanged_by_the_library():
+    """No entry of the C ABI may leave a different CUDA device current than the one it found."""
+    import torch
+    if not torch.cuda.is_available():
+        yield
+        return
+    torch.cuda.set_device(0)
+    yield
+    assert torch.cuda.current_device() == 0, "a library call left another CUDA device current"
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -605,6 +617,7 @@ def test_peer_exchange_ring_on_one_gpu(lv, torch_cuda):
     """G ranks in one process on one GPU (raw pointers instead of IPC): over many more steps than the ring is deep,
     every rank's table of every step holds every rank's block, and no wait ever gives up."""
     torch = torch_cuda
+    torch.cuda.set_device(0)                        # an earlier multi-GPU test may have left another device current
     G, words, depth, steps = 3, 20, 4, 23           # 20 words: the scalar copy path; not a multiple of the ring
     xs = _local_exchanges(G, words, depth)
     streams = [torch.cuda.Stream() for _ in range(G)]
@@ -648,6 +661,7 @@ def test_sharded_step_async_over_peer_exchange_equals_single_rank(lv, orc, torch
     single rank computes, step after step, across more steps than the ring is deep; out['summary'] keeps the local
     block."""
     torch = torch_cuda
+    torch.cuda.set_device(0)
     from livevideo_b200.shard import PeerExchange, ShardedContext, max_shard, shard_range
     w, h, S, T, G, steps = 64, 48, 5, 3, 2, 11
     frames = [orc.gen_batch("camera", 7 + k, S, T, w, h) for k in range(steps)]
@@ -725,3 +739,18 @@ def test_legacy_entries_from_several_threads_and_registered_buffers(lv, orc, tor
         [t.start() for t in ths]
         [t.join() for t in ths]
     assert not errors, errors
+    # the calling thread's stream and scratch stay on the device of its first call even when something else in the
+    # process makes another device current in between
+    torch = torch_cuda
+    if torch.cuda.device_count() >= 2:
+        cur = frames[0, 1]
+        dst = np.zeros(3 * px, np.uint8)
+        csc.YV12_to_RGB24(cur[:px].copy(), cur[px:px + px // 4].copy(), cur[px + px // 4:].copy(), dst, w, h)
+        torch.cuda.set_device(1)
+        try:
+            dst2 = np.zeros(3 * px, np.uint8)
+            csc.YV12_to_RGB24(cur[:px].copy(), cur[px:px + px // 4].copy(), cur[px + px // 4:].copy(), dst2, w, h)
+            assert torch.cuda.current_device() == 1
+        finally:
+            torch.cuda.set_device(0)
+        assert np.array_equal(dst, dst2) and np.array_equal(dst, ref["bgr"][3 * px:6 * px])
