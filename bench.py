@@ -389,6 +389,8 @@ def run_ours(args):
     if world > 1:
         line["config"]["summary_exchange"] = ("peer-memory pushes over NVLink (lv_exchange_*), no per-step collective"
                                               if sc.exchange is not None else "NCCL all_gather_into_tensor per step")
+        if sc.exchange is None and args.exchange == "p2p":
+            line["config"]["summary_exchange"] += f" (peer exchange unavailable: {sc.exchange_error})"
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

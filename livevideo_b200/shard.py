@@ -244,7 +244,7 @@ class ShardedContext:
         self._gathered = [None] * self.RING
         self._k = 0
         self.exchange = None
-        self._max_frames = None
+        self.exchange_error = None
         if exchange == "p2p":
             self._want_p2p = True
         else:
@@ -258,12 +258,49 @@ class ShardedContext:
             raise ValueError("exchange does not match this shard (world, rank, depth)")
         self.exchange = x
 
-    def _make_exchange(self, n_frames, group=None):
+    def enable_peer_exchange(self, n_frames, group=None) -> bool:
+        """Create this rank's exchange sized for `n_frames`, swap CUDA IPC handles over `group` and map the peers.
+        Collective: every rank must call it.  Returns False on EVERY rank -- and leaves the all-gather path in place --
+        when any rank could not allocate, export or map (e.g. CUDA IPC not permitted between the processes)."""
+        import torch
+        import torch.distributed as dist
+
+        def all_ok(ok):
+            dev = torch.device("cuda", self.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(int(t.item()))
+
         cap = max_shard(self.total_streams, self.world)
         words = (cap * n_frames * 2 + 3) & ~3
-        x = PeerExchange(self.device, self.rank, self.world, words, depth=self.RING)
-        x.connect_group(group)
+        x, handle = None, b""
+        try:
+            x = PeerExchange(self.device, self.rank, self.world, words, depth=self.RING)
+            handle = x.handle()
+        except Exception as e:  # noqa: BLE001
+            self.exchange_error = repr(e)
+            x = None
+        if not all_ok(x is not None):
+            if x is not None:
+                x.close()
+            return False
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        ok = True
+        try:
+            x.connect(handles)
+        except Exception as e:  # noqa: BLE001
+            self.exchange_error = repr(e)
+            ok = False
+        if not all_ok(ok):          # also the barrier: nobody publishes into a peer that has not finished mapping
+            x.close()
+            return False
         self._attach_exchange(x)
+        return True
+
+    def _make_exchange(self, n_frames, group=None):
+        if not self.enable_peer_exchange(n_frames, group):
+            self._want_p2p = False      # stay on the library all-gather
 
     def _step_async_p2p(self, i420_local, n_frames, out):
         import torch
@@ -289,6 +326,8 @@ class ShardedContext:
         import torch.distributed as dist
         if self.exchange is None and self._want_p2p and self.world > 1:
             self._make_exchange(n_frames, group)
+        if self.exchange is not None and self.local_streams * n_frames * 2 > self.exchange.slot_words:
+            raise ValueError("n_frames larger than the peer exchange was sized for")
         if self.exchange is not None:
             return self._step_async_p2p(i420_local, n_frames, out)
         self.ctx.convert_diff_batch(i420_local, self.local_streams, n_frames, out)

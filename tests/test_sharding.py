@@ -63,6 +63,15 @@ def _worker(rank, world, port, n_streams, n_frames, w, h, q):
         pend = [gather_summaries_async(local, n_streams, n_frames) for _ in range(3)]   # several in flight
         for p in pend:
             assert torch.equal(p.result(), full)
+        # the peer-memory exchange cannot be set up without a GPU: every rank must learn that together (no rank may
+        # hang in the handle swap) and stay on the all-gather
+        from livevideo_b200.shard import ShardedContext
+        sc = ShardedContext.__new__(ShardedContext)
+        sc.total_streams, sc.rank, sc.world, sc.device = n_streams, rank, world, 0
+        sc.exchange, sc.exchange_error = None, None
+        if not torch.cuda.is_available():
+            assert sc.enable_peer_exchange(n_frames) is False
+            assert sc.exchange is None and "LiveVideoError" in sc.exchange_error
         q.put((rank, full.numpy().copy()))
     finally:
         dist.destroy_process_group()
