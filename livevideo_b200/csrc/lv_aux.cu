@@ -190,7 +190,14 @@ constexpr int kBoxUnroll = 4;
 template <bool kBits>
 __device__ __forceinline__ uint4 box_load(const uint8_t *mask, size_t row_bytes, int w, int y, int c)
 {
-    if (!kBits) return __ldg(reinterpret_cast<const uint4 *>(mask + (size_t)y * row_bytes + (size_t)c * 16));
+    if (!kBits) {
+        // volatile asm: ptxas otherwise re-uses the destination registers and serialises load -> use -> load
+        uint4 v;
+        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(mask + (size_t)y * row_bytes + (size_t)c * 16));
+        return v;
+    }
     // a row of the bit mask is w/16 uint16 units = w/8 bytes: rows need not be 16-byte aligned and the last item of a
     // row may be short
     const uint8_t *p = mask + (size_t)y * row_bytes + (size_t)c * 16;
@@ -205,7 +212,7 @@ __device__ __forceinline__ uint4 box_load(const uint8_t *mask, size_t row_bytes,
 }
 
 template <bool kBits>
-__global__ void __launch_bounds__(256) k_object_box(const uint8_t *__restrict__ mask, int w, size_t frame_stride, int x0, int x1,
+__global__ void __launch_bounds__(256, 2) k_object_box(const uint8_t *__restrict__ mask, int w, size_t frame_stride, int x0, int x1,
                                                     int y0, int y1, int rows_per_block, int *boxes)
 {
     mask += (size_t)blockIdx.y * frame_stride;
@@ -236,11 +243,13 @@ __global__ void __launch_bounds__(256) k_object_box(const uint8_t *__restrict__ 
             uint4 acc = make_uint4(0u, 0u, 0u, 0u);
             for (int y = rb0 + q; y < rb1; y += kBoxUnroll * rpp) {
                 uint4 v[kBoxUnroll];
+                int yc[kBoxUnroll];
 #pragma unroll
-                for (int k = 0; k < kBoxUnroll; k++) {
-                    const int yk = y + k * rpp;
-                    v[k] = yk < rb1 ? box_load<kBits>(mask, row_bytes, w, yk, c) : make_uint4(0u, 0u, 0u, 0u);
-                }
+                for (int k = 0; k < kBoxUnroll; k++)      // unconditional (row clamped) so that all loads are issued before any use
+                    yc[k] = min(y + k * rpp, rb1 - 1);
+#pragma unroll
+                for (int k = 0; k < kBoxUnroll; k++)
+                    v[k] = box_load<kBits>(mask, row_bytes, w, yc[k], c);
 #pragma unroll
                 for (int k = 0; k < kBoxUnroll; k++) {
                     uint4 m;
@@ -251,9 +260,8 @@ __global__ void __launch_bounds__(256) k_object_box(const uint8_t *__restrict__ 
                                        eq1_bits(v[k].w, clip[3]));
                     }
                     if ((m.x | m.y | m.z | m.w) != 0u) {
-                        const int yk = y + k * rpp;            // only reached for rows inside the band (padding has no set pixel)
-                        mny = min(mny, yk);
-                        mxy = max(mxy, yk);
+                        mny = min(mny, yc[k]);                  // a clamped duplicate of the band's last row changes nothing
+                        mxy = max(mxy, yc[k]);
                     }
                     acc.x |= m.x; acc.y |= m.y; acc.z |= m.z; acc.w |= m.w;
                 }
@@ -338,10 +346,13 @@ int launch_object_box(int w, int h, const uint8_t *mask, bool bits, int n_frames
             } else {
                 const int per = bits ? 128 : 16;
                 const int cols = x1 / per - x0 / per + 1, cpb = cols < 256 ? cols : 256, rpp = 256 / cpb;
-                // a band = 2 passes of kBoxUnroll x rpp rows; fewer, taller bands when that would be too many blocks
-                long long rpb = 2LL * 4 * rpp;
-                const long long cap = (16LL * 148 * 8 + nf - 1) / nf;
-                if ((rows + rpb - 1) / rpb > cap) rpb = (rows + cap - 1) / cap;
+                // One wave: at most 148 SMs x 8 resident blocks in the whole launch, so every block is loading from the
+                // first microsecond and its fixed costs (set-up, reduction, the bound pre-read and atomics) are paid once
+                // per many passes; a band is at least one pass of kBoxUnroll x rpp rows.
+                long long bands = (rows + 4LL * rpp - 1) / (4LL * rpp);
+                const long long cap = (148LL * 8) / nf > 0 ? (148LL * 8) / nf : 1;
+                if (bands > cap) bands = cap;
+                const long long rpb = (rows + bands - 1) / bands;
                 const unsigned bx = (unsigned)((rows + rpb - 1) / rpb);
                 if (bits) k_object_box<true><<<dim3(bx, nf), 256, 0, st>>>(m, w, stride, x0, x1, y0, y1, (int)rpb, boxes);
                 else k_object_box<false><<<dim3(bx, nf), 256, 0, st>>>(m, w, stride, x0, x1, y0, y1, (int)rpb, boxes);

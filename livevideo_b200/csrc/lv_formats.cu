@@ -199,7 +199,7 @@ __device__ __forceinline__ uint2 pick8(const uint4 &a, const uint4 &b, int sel)
 }
 
 // kind 2, YVU9 -> YV12: work item = 32 luma pixels x 4 rows (+ 8 chroma samples of each plane -> 16 x 2 rows)
-__global__ void __launch_bounds__(256) k_yvu9_to_yv12_v(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h,
+__global__ void __launch_bounds__(256, 4) k_yvu9_to_yv12_v(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h,
                                                         size_t in_frame, size_t out_frame)
 {
     const size_t px = (size_t)w * h;
@@ -208,19 +208,27 @@ __global__ void __launch_bounds__(256) k_yvu9_to_yv12_v(const uint8_t *__restric
     const int upr = w >> 5, items = upr * (h >> 2), cw2 = w >> 1, cw4 = w >> 2, ch4 = h >> 2;
     for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
         const int q = it / upr, u = it - q * upr;
+        // every load of the item is issued before the first store (10 in flight per thread)
+        uint4 v0[4], v1[4];
+        uint2 c[2];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            const int y = 4 * q + r;
-            const uint8_t *src = in + (size_t)(h - 1 - y) * w + 32 * u;        // planes are read bottom-up
-            uint8_t *dst = out + (size_t)y * w + 32 * u;
-            const uint4 v0 = ldg16(src), v1 = ldg16(src + 16);
-            stg16(dst, v0);
-            stg16(dst + 16, v1);
+            const uint8_t *src = in + (size_t)(h - 1 - (4 * q + r)) * w + 32 * u;      // planes are read bottom-up
+            v0[r] = ldg16(src);
+            v1[r] = ldg16(src + 16);
+        }
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++)
+            c[pl] = ldg8(in + px + (size_t)pl * ((size_t)cw4 * ch4) + (size_t)(ch4 - 1 - q) * cw4 + 8 * u);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            uint8_t *dst = out + (size_t)(4 * q + r) * w + 32 * u;
+            stg16(dst, v0[r]);
+            stg16(dst + 16, v1[r]);
         }
 #pragma unroll
         for (int pl = 0; pl < 2; pl++) {
-            const uint2 c = ldg8(in + px + (size_t)pl * ((size_t)cw4 * ch4) + (size_t)(ch4 - 1 - q) * cw4 + 8 * u);
-            const uint4 d = dup8(c);
+            const uint4 d = dup8(c[pl]);
             uint8_t *dst = out + px + (size_t)pl * (px / 4) + (size_t)(2 * q) * cw2 + 16 * u;
             stg16(dst, d);
             stg16(dst + cw2, d);
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(256) k_yuy2_to_yv12_v(const uint8_t *__restric
 }
 
 // kind 4, YV12 -> YVU9: work item = 32 luma pixels x 4 rows (+ 16 chroma samples of an even row -> 8)
-__global__ void __launch_bounds__(256) k_yv12_to_yvu9_v(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h,
+__global__ void __launch_bounds__(256, 4) k_yv12_to_yvu9_v(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h,
                                                         size_t in_frame, size_t out_frame)
 {
     const size_t px = (size_t)w * h;
@@ -260,18 +268,25 @@ __global__ void __launch_bounds__(256) k_yv12_to_yvu9_v(const uint8_t *__restric
     const int upr = w >> 5, items = upr * (h >> 2), cw2 = w >> 1, cw4 = w >> 2, ch4 = h >> 2;
     for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
         const int q = it / upr, u = it - q * upr;
+        uint4 v0[4], v1[4], c[2];                 // loads first, then stores
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const size_t o = (size_t)(4 * q + r) * w + 32 * u;
-            const uint4 v0 = ldg16(in + o), v1 = ldg16(in + o + 16);
-            stg16(out + o, v0);
-            stg16(out + o + 16, v1);
+            v0[r] = ldg16(in + o);
+            v1[r] = ldg16(in + o + 16);
         }
 #pragma unroll
-        for (int pl = 0; pl < 2; pl++) {
-            const uint4 c = ldg16(in + px + (size_t)pl * (px / 4) + (size_t)(2 * q) * cw2 + 16 * u);
-            stg8(out + px + (size_t)pl * ((size_t)cw4 * ch4) + (size_t)q * cw4 + 8 * u, even8(c));
+        for (int pl = 0; pl < 2; pl++)
+            c[pl] = ldg16(in + px + (size_t)pl * (px / 4) + (size_t)(2 * q) * cw2 + 16 * u);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const size_t o = (size_t)(4 * q + r) * w + 32 * u;
+            stg16(out + o, v0[r]);
+            stg16(out + o + 16, v1[r]);
         }
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++)
+            stg8(out + px + (size_t)pl * ((size_t)cw4 * ch4) + (size_t)q * cw4 + 8 * u, even8(c[pl]));
     }
 }
 
