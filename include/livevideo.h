@@ -151,6 +151,16 @@ LV_API int lv_object_box(lv_ctx *ctx, const void *d_mask, int mask_is_bits, int 
 LV_API int lv_object_box_batch(lv_ctx *ctx, const void *d_mask, int mask_is_bits, int n_frames, int x0, int x1, int y0,
                                int y1, int *d_boxes, void *cuda_stream);
 
+/* The GPU side of the producer hook.  write_out_picture (lib/JM/output.c:362-453) narrows the
+ * decoder's unsigned-short planes (imgpel, lib/JM/global.h:61) to bytes and cuts the crop rectangle away with one
+ * memcpy per SAMPLE (img2buf, output.c:161-176: the low byte of the little-endian short, no clipping).  Here the host
+ * only block-copies the raw planes (each is one contiguous allocation, memalloc.c:26-39) and the device does the rest:
+ * d_pic16 = n_frames pictures, each Y16[size_x*size_y] U16[(size_x/2)*(size_y/2)] V16[...] (U = imgUV[0], V = imgUV[1]);
+ * d_i420 = n_frames tight I420 frames of the context's geometry, whose rectangle starts at (crop_left, crop_top) of the
+ * picture (luma pixels, even: twice the SPS offsets, output.c:375-380; the chroma planes use half, output.c:421-425). */
+LV_API int lv_narrow_pictures(lv_ctx *ctx, const uint16_t *d_pic16, int n_frames, int size_x, int size_y,
+                              int crop_left, int crop_top, uint8_t *d_i420, void *cuda_stream);
+
 /* Device-pointer form of the five converters above: kind 1 RGB24_to_YV12, 2 YVU9_to_YV12, 3 YUY2_to_YV12,
  * 4 YV12_to_YVU9, 5 YV12_to_YUY2; n_frames frames back to back (bytes per frame: lv_format_bytes). */
 LV_API int lv_convert_format(lv_ctx *ctx, int kind, const uint8_t *d_in, uint8_t *d_out, int n_frames, void *cuda_stream);
@@ -182,6 +192,12 @@ LV_API int lv_host_unregister(void *p);
 LV_API int lv_step_host(lv_ctx *ctx, const uint8_t *h_i420, int first_stream, int n_streams, int n_frames,
                         uint8_t *h_bgr, uint16_t *h_mask_bits, uint16_t *h_mb_count, uint8_t *h_mb_map,
                         uint32_t *h_summary);
+/* The same step fed with the decoder's own pictures instead of I420 frames: h_pic16 holds n_streams*n_frames pictures
+ * (stream-major) in the lv_narrow_pictures layout; the narrowing + cropping of lib/JM/output.c:87-178, 362-453 runs on
+ * the device in front of the fused kernel of every chunk, so the producer hook is three block copies per picture. */
+LV_API int lv_step_host_pictures(lv_ctx *ctx, const uint16_t *h_pic16, int size_x, int size_y, int crop_left, int crop_top,
+                                 int first_stream, int n_streams, int n_frames, uint8_t *h_bgr, uint16_t *h_mask_bits,
+                                 uint16_t *h_mb_count, uint8_t *h_mb_map, uint32_t *h_summary);
 
 /* ---- synthetic input (benchmark / tests): stands in for the JM decoder's output --------------------
  * kind 0 = `uniform`, 1 = `camera`; writes n_streams*n_frames I420 frames, stream-major,

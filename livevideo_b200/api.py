@@ -253,6 +253,16 @@ class Context:
             1 if mask_is_bits else 0, x0, x1, y0, y1, box.data_ptr(), _stream_handle(cuda_stream)), "lv_object_box")
         return tuple(int(v) for v in box.cpu())
 
+    def narrow_pictures(self, pic16, n_frames, size_x, size_y, crop_left, crop_top, out_i420, cuda_stream=None):
+        """Decoder pictures (int16 CUDA tensor: Y16, U16, V16 planes per picture) -> tight 8-bit I420 frames of this
+        context's geometry: the reference's img2buf + write_out_picture (lib/JM/output.c:87-178, 362-453)."""
+        import torch
+        samples = size_x * size_y + 2 * ((size_x // 2) * (size_y // 2))
+        capi.check(capi.lib().lv_narrow_pictures(
+            self._h, _dev_ptr(pic16, torch.int16, n_frames * samples, "pic16", self.device), n_frames, size_x, size_y,
+            crop_left, crop_top, _dev_ptr(out_i420, torch.uint8, n_frames * self.frame_bytes, "out_i420", self.device),
+            _stream_handle(cuda_stream)), "lv_narrow_pictures")
+
     def object_box_batch(self, masks, n_frames, x0, x1, y0, y1, mask_is_bits=False, cuda_stream=None):
         """One box per frame for n_frames masks laid out back to back: int32 CUDA tensor [n_frames, 4]."""
         import torch
@@ -302,6 +312,22 @@ class Context:
             p(bgr, np.uint8, n * self.bgr_bytes, "bgr"), p(mask_bits, np.uint16, 2 * n * self.mask_units, "mask_bits"),
             p(mb_count, np.uint16, 2 * n * self.mbs, "mb_count"), p(mb_map, np.uint8, n * self.mbs, "mb_map"),
             p(summary, np.uint32, 8 * n, "summary")), "lv_step_host")
+
+    def step_host_pictures(self, pic16, size_x, size_y, crop_left, crop_top, n_streams, n_frames, bgr=None, mask_bits=None,
+                           mb_count=None, mb_map=None, summary=None, first_stream=0):
+        """step_host fed with the decoder's own pictures (numpy uint16: Y16, U16, V16 planes per picture): the narrowing
+        and cropping of lib/JM/output.c:87-178, 362-453 runs on the device in front of the fused kernel."""
+        n = n_streams * n_frames
+        samples = size_x * size_y + 2 * ((size_x // 2) * (size_y // 2))
+
+        def p(a, dt, nb, name, w=True):
+            return None if a is None else _host_ptr(a, dt, nb, name, w)
+        capi.check(capi.lib().lv_step_host_pictures(
+            self._h, _host_ptr(pic16, np.uint16, 2 * n * samples, "pic16"), size_x, size_y, crop_left, crop_top,
+            first_stream, n_streams, n_frames,
+            p(bgr, np.uint8, n * self.bgr_bytes, "bgr"), p(mask_bits, np.uint16, 2 * n * self.mask_units, "mask_bits"),
+            p(mb_count, np.uint16, 2 * n * self.mbs, "mb_count"), p(mb_map, np.uint8, n * self.mbs, "mb_map"),
+            p(summary, np.uint32, 8 * n, "summary")), "lv_step_host_pictures")
 
 
 class _DevView:

@@ -39,6 +39,7 @@ SYMBOLS = {
     "lv_write_bks": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "lv_object_box": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "lv_object_box_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "lv_narrow_pictures": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "lv_upload_async": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "lv_upload_wait": (C.c_int, [_vp, C.c_int, _vp]),
     "lv_upload_release": (C.c_int, [_vp, C.c_int, _vp]),
@@ -49,6 +50,8 @@ SYMBOLS = {
     "lv_host_register": (C.c_int, [_vp, C.c_size_t]),
     "lv_host_unregister": (C.c_int, [_vp]),
     "lv_step_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "lv_step_host_pictures": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp,
+                                        _vp, _vp, _vp]),
     "lv_shard_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "lv_shard_destroy": (None, [_vp]),
     "lv_shard_device_count": (C.c_int, [_vp]),

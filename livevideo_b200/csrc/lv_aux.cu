@@ -291,6 +291,91 @@ __global__ void k_box_init(int *boxes, int n, int x0, int x1, int y0, int y1)
     if (f < n) reinterpret_cast<int4 *>(boxes)[f] = make_int4(x1 + 1, x0 - 1, y1 + 1, y0 - 1);
 }
 
+// ---- decoder picture (unsigned-short planes) -> tight 8-bit I420: img2buf + write_out_picture on the GPU ----------------
+// lib/JM/output.c:87-178: with imgpel == unsigned short (global.h:61) and 1-byte output symbols the reference copies ONE
+// byte of every little-endian sample -- its low byte, no clipping -- and cuts the crop rectangle away, sample by sample;
+// write_out_picture (output.c:362-453) does that for Y, then imgUV[0], then imgUV[1], the chroma planes with half the
+// luma crop.  3 B/px in (16-bit 4:2:0) + 1.5 B/px out.
+struct NarrowArgs {
+    const uint16_t *pic16;
+    uint8_t *i420;
+    int size_x, size_y, crop_left, crop_top, w, h;
+    size_t pic_samples, frame;       // strides between pictures (samples) and between output frames (bytes)
+};
+
+// item = 16 output bytes of one plane row; kNarrowUnroll items (2 x 16-byte loads each) in flight per thread
+constexpr int kNarrowUnroll = 4;
+
+__device__ __forceinline__ void narrow_addr(const NarrowArgs &a, int i, int ny, int nc, const uint16_t *pic, uint8_t *out,
+                                            const uint16_t *&src, uint8_t *&dst)
+{
+    if (i < ny) {
+        const int per = a.w >> 4, row = i / per, col = i - row * per;
+        src = pic + (size_t)(row + a.crop_top) * a.size_x + a.crop_left + 16 * col;
+        dst = out + (size_t)row * a.w + 16 * col;
+    } else {
+        int j = i - ny;
+        const int pl = j >= nc;
+        j -= pl * nc;
+        const int cw = a.w >> 1, cx = a.size_x >> 1, cy = a.size_y >> 1;
+        const int per = cw >> 4, row = j / per, col = j - row * per;
+        src = pic + (size_t)a.size_x * a.size_y + (size_t)pl * cx * cy + (size_t)(row + (a.crop_top >> 1)) * cx +
+              (a.crop_left >> 1) + 16 * col;
+        dst = out + (size_t)a.w * a.h + (size_t)pl * cw * (a.h >> 1) + (size_t)row * cw + 16 * col;
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) k_narrow_v(const NarrowArgs a)
+{
+    const uint16_t *pic = a.pic16 + (size_t)blockIdx.y * a.pic_samples;
+    uint8_t *out = a.i420 + (size_t)blockIdx.y * a.frame;
+    const int ny = (a.w >> 4) * a.h, nc = (a.w >> 5) * (a.h >> 1), total = ny + 2 * nc;
+    const int base = blockIdx.x * (256 * kNarrowUnroll) + threadIdx.x;
+    uint4 lo[kNarrowUnroll], hi[kNarrowUnroll];
+    uint8_t *dst[kNarrowUnroll];
+#pragma unroll
+    for (int k = 0; k < kNarrowUnroll; k++) {
+        const int i = min(base + 256 * k, total - 1);        // clamped: every load is issued, the store is guarded
+        const uint16_t *src;
+        narrow_addr(a, i, ny, nc, pic, out, src, dst[k]);
+        lo[k] = __ldcs(reinterpret_cast<const uint4 *>(src));
+        hi[k] = __ldcs(reinterpret_cast<const uint4 *>(src) + 1);
+    }
+#pragma unroll
+    for (int k = 0; k < kNarrowUnroll; k++) {
+        if (base + 256 * k < total) {
+            // low byte of every little-endian short: bytes 0, 2 of each word
+            const uint4 o = make_uint4(__byte_perm(lo[k].x, lo[k].y, 0x6420u), __byte_perm(lo[k].z, lo[k].w, 0x6420u),
+                                       __byte_perm(hi[k].x, hi[k].y, 0x6420u), __byte_perm(hi[k].z, hi[k].w, 0x6420u));
+            __stcs(reinterpret_cast<uint4 *>(dst[k]), o);
+        }
+    }
+}
+
+// any legal geometry: one thread per output byte
+__global__ void __launch_bounds__(256) k_narrow_scalar(const NarrowArgs a)
+{
+    const uint16_t *pic = a.pic16 + (size_t)blockIdx.y * a.pic_samples;
+    uint8_t *out = a.i420 + (size_t)blockIdx.y * a.frame;
+    const size_t px = (size_t)a.w * a.h, cpx = (size_t)(a.w >> 1) * (a.h >> 1);
+    const int cx = a.size_x >> 1, cy = a.size_y >> 1, cw = a.w >> 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.frame; i += (size_t)gridDim.x * blockDim.x) {
+        uint16_t v;
+        if (i < px) {
+            const int row = (int)(i / a.w), col = (int)(i - (size_t)row * a.w);
+            v = pic[(size_t)(row + a.crop_top) * a.size_x + a.crop_left + col];
+        } else {
+            size_t j = i - px;
+            const int pl = j >= cpx;
+            j -= pl * cpx;
+            const int row = (int)(j / cw), col = (int)(j - (size_t)row * cw);
+            v = pic[(size_t)a.size_x * a.size_y + (size_t)pl * cx * cy + (size_t)(row + (a.crop_top >> 1)) * cx +
+                    (a.crop_left >> 1) + col];
+        }
+        out[i] = (uint8_t)(v & 0xffu);
+    }
+}
+
 }  // namespace
 
 int launch_write_bks(const Geom &g, const uint8_t *cur, const uint8_t *bkd, int n_frames, int tol, uint8_t *out,
@@ -361,6 +446,37 @@ int launch_object_box(int w, int h, const uint8_t *mask, bool bits, int n_frames
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return -(int)e;
+    }
+    return launches;
+}
+
+int launch_narrow(const Geom &g, const uint16_t *pic16, int n_frames, int size_x, int size_y, int crop_left, int crop_top,
+                  uint8_t *i420, cudaStream_t st)
+{
+    if (n_frames <= 0) return 0;
+    NarrowArgs a{};
+    a.size_x = size_x; a.size_y = size_y; a.crop_left = crop_left; a.crop_top = crop_top; a.w = g.w; a.h = g.h;
+    a.pic_samples = (size_t)size_x * size_y + 2 * ((size_t)(size_x >> 1) * (size_y >> 1));
+    a.frame = g.frame;
+    const bool vec = g.w % 32 == 0 && size_x % 16 == 0 && crop_left % 16 == 0 && ((size_t)size_x * size_y) % 8 == 0 &&
+                     ((size_t)(size_x >> 1) * (size_y >> 1)) % 8 == 0 && g.frame % 16 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(pic16) | reinterpret_cast<uintptr_t>(i420)) & 15) == 0;
+    int launches = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += 65535) {
+        const int nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
+        a.pic16 = pic16 + (size_t)f0 * a.pic_samples;
+        a.i420 = i420 + (size_t)f0 * g.frame;
+        if (vec) {
+            const int total = (g.w >> 4) * g.h + 2 * ((g.w >> 5) * (g.h >> 1));
+            k_narrow_v<<<dim3((total + 256 * kNarrowUnroll - 1) / (256 * kNarrowUnroll), nf), 256, 0, st>>>(a);
+        } else {
+            unsigned bx = (unsigned)((g.frame + 255) / 256);
+            if (bx > 4096) bx = 4096;
+            k_narrow_scalar<<<dim3(bx, nf), 256, 0, st>>>(a);
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return -(int)e;
+        launches++;
     }
     return launches;
 }

@@ -59,6 +59,8 @@ struct lv_ctx {
     uint32_t *d_sum[kSlots] = {};
     cudaEvent_t ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
     int slot_frames = 0;                      // capacity of one slot in frames
+    uint16_t *d_pic[kSlots] = {};             // lv_step_host_pictures: raw 16-bit pictures of a chunk
+    size_t pic_cap = 0;                       // capacity of one d_pic slot in samples
     // stand-alone upload slots (lv_upload_async)
     cudaStream_t s_upload = nullptr;
     uint8_t *d_up[2] = {nullptr, nullptr};
@@ -88,6 +90,7 @@ bool geom_fast(int w, int h) { return w >= 16 && h >= 2 && w % 16 == 0 && h % 2 
 void free_pipeline(lv_ctx *c)
 {
     for (int i = 0; i < lv_ctx::kSlots; i++) {
+        cudaFree(c->d_pic[i]); c->d_pic[i] = nullptr;
         cudaFree(c->d_in[i]); cudaFree(c->d_bgr[i]); cudaFree(c->d_bits[i]); cudaFree(c->d_cnt[i]);
         cudaFree(c->d_map[i]); cudaFree(c->d_sum[i]);
         c->d_in[i] = c->d_bgr[i] = c->d_map[i] = nullptr; c->d_bits[i] = c->d_cnt[i] = nullptr; c->d_sum[i] = nullptr;
@@ -101,6 +104,7 @@ void free_pipeline(lv_ctx *c)
     if (c->s_copy_out) cudaStreamDestroy(c->s_copy_out);
     c->s_copy_in = c->s_compute = c->s_copy_out = nullptr;
     c->slot_frames = 0;
+    c->pic_cap = 0;
 }
 
 // Device slots for the host step: `frames` frames each.
@@ -353,6 +357,21 @@ int lv_object_box(lv_ctx *c, const void *d_mask, int mask_is_bits, int x0, int x
     return lv_object_box_batch(c, d_mask, mask_is_bits, 1, x0, x1, y0, y1, d_box4, cuda_stream);
 }
 
+int lv_narrow_pictures(lv_ctx *c, const uint16_t *d_pic16, int n_frames, int size_x, int size_y, int crop_left, int crop_top,
+                       uint8_t *d_i420, void *cuda_stream)
+{
+    if (!c || !d_pic16 || !d_i420 || n_frames < 0) return LV_E_ARG;
+    // 4:2:0 pictures: even sizes, even luma crops (twice the SPS offsets, lib/JM/output.c:375-380), crop inside the picture
+    if (size_x <= 0 || size_y <= 0 || (size_x & 1) || (size_y & 1) || crop_left < 0 || crop_top < 0 || (crop_left & 1) ||
+        (crop_top & 1) || crop_left + c->g.w > size_x || crop_top + c->g.h > size_y)
+        return LV_E_SIZE;
+    if ((reinterpret_cast<uintptr_t>(d_pic16) & 1) != 0) return LV_E_ARG;
+    if (n_frames == 0) return LV_OK;
+    DeviceGuard guard(c->device);
+    return launch_result(lv::launch_narrow(c->g, d_pic16, n_frames, size_x, size_y, crop_left, crop_top, d_i420,
+                                           (cudaStream_t)cuda_stream), c->launches);
+}
+
 int lv_convert_format(lv_ctx *c, int kind, const uint8_t *d_in, uint8_t *d_out, int n_frames, void *cuda_stream)
 {
     if (!c || !d_in || !d_out || kind < 1 || kind > 5 || n_frames < 0) return LV_E_ARG;
@@ -465,10 +484,31 @@ int lv_host_unregister(void *p)
 //   compute stream : kernel chunk k       (waits for its H2D)
 //   copy-out stream: D2H chunk k          (waits for its kernel)
 // With 3 slots the upload of k+1, the kernel of k and the download of k-1 are in flight together.
-int lv_step_host(lv_ctx *c, const uint8_t *h_i420, int first_stream, int n_streams, int n_frames, uint8_t *h_bgr,
-                 uint16_t *h_mask_bits, uint16_t *h_mb_count, uint8_t *h_mb_map, uint32_t *h_summary)
+namespace {
+// optional 16-bit source of the host step (lv_step_host_pictures): decoder pictures instead of I420 frames
+struct PicSource {
+    const uint16_t *h_pic16;
+    int size_x, size_y, crop_left, crop_top;
+    size_t samples;              // per picture
+};
+
+int ensure_pic_slots(lv_ctx *c, size_t samples)
 {
-    if (!c || !h_i420) return LV_E_ARG;
+    if (c->pic_cap >= samples) return LV_OK;
+    for (int i = 0; i < lv_ctx::kSlots; i++) {
+        LV_CUDA(cudaStreamSynchronize(c->s_compute));
+        cudaFree(c->d_pic[i]);
+        c->d_pic[i] = nullptr;
+        LV_CUDA(cudaMalloc(&c->d_pic[i], samples * sizeof(uint16_t)));
+    }
+    c->pic_cap = samples;
+    return LV_OK;
+}
+
+int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int first_stream, int n_streams, int n_frames,
+                   uint8_t *h_bgr, uint16_t *h_mask_bits, uint16_t *h_mb_count, uint8_t *h_mb_map, uint32_t *h_summary)
+{
+    if (!c || (!h_i420 && !pic)) return LV_E_ARG;
     if (n_streams < 0 || n_frames < 0 || first_stream < 0 || first_stream + n_streams > c->max_streams) return LV_E_ARG;
     if (!geom_fast(c->g.w, c->g.h)) return LV_E_SIZE;
     if (n_streams == 0 || n_frames == 0) return LV_OK;
@@ -483,7 +523,8 @@ int lv_step_host(lv_ctx *c, const uint8_t *h_i420, int first_stream, int n_strea
         const long mb = e ? atol(e) : 0;
         chunk_bytes = (size_t)(mb > 0 && mb <= 1024 ? mb : LV_HOST_CHUNK_MB_DEFAULT) << 20;
     }
-    int cf = (int)(chunk_bytes / (g.frame * (size_t)n_streams));
+    const size_t in_frame = pic ? pic->samples * sizeof(uint16_t) : g.frame;     // host bytes per frame
+    int cf = (int)(chunk_bytes / (in_frame * (size_t)n_streams));
     if (cf < 1) cf = 1;
     if (cf > n_frames) cf = n_frames;
     // a slot must hold one chunk; streams are cut too if even one frame of all streams is too large
@@ -492,6 +533,10 @@ int lv_step_host(lv_ctx *c, const uint8_t *h_i420, int first_stream, int n_strea
     if ((size_t)cs * cf > cap_frames) { cf = 1; if ((size_t)cs > cap_frames) cs = (int)cap_frames; }
     int rc = ensure_pipeline(c, cs * cf);
     if (rc != LV_OK) return rc;
+    if (pic) {
+        rc = ensure_pic_slots(c, pic->samples * (size_t)cs * cf);
+        if (rc != LV_OK) return rc;
+    }
 
     int k = 0;
     for (int s0 = 0; s0 < n_streams; s0 += cs) {
@@ -506,12 +551,21 @@ int lv_step_host(lv_ctx *c, const uint8_t *h_i420, int first_stream, int n_strea
             }
             // H2D: per stream one strided piece (frames t0..t0+nt of stream s are contiguous in the host batch)
             for (int s = 0; s < ns; s++) {
-                const uint8_t *src = h_i420 + ((size_t)(s0 + s) * n_frames + t0) * g.frame;
-                LV_CUDA(cudaMemcpyAsync(c->d_in[slot] + (size_t)s * nt * g.frame, src, (size_t)nt * g.frame,
-                                        cudaMemcpyHostToDevice, c->s_copy_in));
+                const size_t hf = (size_t)(s0 + s) * n_frames + t0, df = (size_t)s * nt;
+                if (pic)
+                    LV_CUDA(cudaMemcpyAsync(c->d_pic[slot] + df * pic->samples, pic->h_pic16 + hf * pic->samples,
+                                            (size_t)nt * pic->samples * sizeof(uint16_t), cudaMemcpyHostToDevice, c->s_copy_in));
+                else
+                    LV_CUDA(cudaMemcpyAsync(c->d_in[slot] + df * g.frame, h_i420 + hf * g.frame, (size_t)nt * g.frame,
+                                            cudaMemcpyHostToDevice, c->s_copy_in));
             }
             LV_CUDA(cudaEventRecord(c->ev_in[slot], c->s_copy_in));
             LV_CUDA(cudaStreamWaitEvent(c->s_compute, c->ev_in[slot], 0));
+            if (pic) {     // img2buf + write_out_picture on the device: 16-bit planes -> the slot's tight I420 frames
+                rc = launch_result(lv::launch_narrow(g, c->d_pic[slot], ns * nt, pic->size_x, pic->size_y, pic->crop_left,
+                                                     pic->crop_top, c->d_in[slot], c->s_compute), c->launches);
+                if (rc != LV_OK) return rc;
+            }
             rc = lv_convert_diff_batch(c, c->d_in[slot], first_stream + s0, ns, nt, h_bgr ? c->d_bgr[slot] : nullptr,
                                        h_mask_bits ? c->d_bits[slot] : nullptr, nullptr,
                                        h_mb_count ? c->d_cnt[slot] : nullptr, h_mb_map ? c->d_map[slot] : nullptr,
@@ -543,6 +597,29 @@ int lv_step_host(lv_ctx *c, const uint8_t *h_i420, int first_stream, int n_strea
     LV_CUDA(cudaStreamSynchronize(c->s_copy_out));
     LV_CUDA(cudaStreamSynchronize(c->s_compute));
     return LV_OK;
+}
+}  // namespace
+
+int lv_step_host(lv_ctx *c, const uint8_t *h_i420, int first_stream, int n_streams, int n_frames, uint8_t *h_bgr,
+                 uint16_t *h_mask_bits, uint16_t *h_mb_count, uint8_t *h_mb_map, uint32_t *h_summary)
+{
+    if (!h_i420) return LV_E_ARG;
+    return step_host_impl(c, h_i420, nullptr, first_stream, n_streams, n_frames, h_bgr, h_mask_bits, h_mb_count, h_mb_map,
+                          h_summary);
+}
+
+int lv_step_host_pictures(lv_ctx *c, const uint16_t *h_pic16, int size_x, int size_y, int crop_left, int crop_top,
+                          int first_stream, int n_streams, int n_frames, uint8_t *h_bgr, uint16_t *h_mask_bits,
+                          uint16_t *h_mb_count, uint8_t *h_mb_map, uint32_t *h_summary)
+{
+    if (!c || !h_pic16) return LV_E_ARG;
+    if (size_x <= 0 || size_y <= 0 || (size_x & 1) || (size_y & 1) || crop_left < 0 || crop_top < 0 || (crop_left & 1) ||
+        (crop_top & 1) || crop_left + c->g.w > size_x || crop_top + c->g.h > size_y)
+        return LV_E_SIZE;
+    PicSource p{h_pic16, size_x, size_y, crop_left, crop_top,
+                (size_t)size_x * size_y + 2 * ((size_t)(size_x >> 1) * (size_y >> 1))};
+    return step_host_impl(c, nullptr, &p, first_stream, n_streams, n_frames, h_bgr, h_mask_bits, h_mb_count, h_mb_map,
+                          h_summary);
 }
 
 // ---- legacy drop-in entries ------------------------------------------------------------------------

@@ -77,6 +77,8 @@ int launch_diff_strip(const DiffArgs &a, cudaStream_t st);
 // lv_aux.cu: background subtraction (WriteBks) and object box
 int launch_write_bks(const Geom &g, const uint8_t *cur, const uint8_t *bkd, int n_frames, int tol, uint8_t *out,
                      uint16_t *obj_bits, cudaStream_t st);
+int launch_narrow(const Geom &g, const uint16_t *pic16, int n_frames, int size_x, int size_y, int crop_left, int crop_top,
+                  uint8_t *i420, cudaStream_t st);
 int launch_object_box(int w, int h, const uint8_t *mask, bool bits, int n_frames, int x0, int x1, int y0, int y1, int *d_boxes,
                       cudaStream_t st);
 

@@ -7,6 +7,10 @@
  *
  *     jm_ldecod  stream.264  out.yuv|-  width height
  *
+ *     jm_ldecod  --img2buf size_x size_y crop_left crop_right crop_top crop_bottom  < plane.u16  > plane.u8
+ *         runs the reference's OWN img2buf (lib/JM/output.c:87-178) with symbol_size_in_bytes = 1 on one imgpel plane
+ *         read from stdin: the known-answer source that pins the oracle's restatement of the narrowing + cropping
+ *
  * Frames leave the decoder through write_out_picture (lib/JM/output.c:362-453): Y, U, V, 8 bit, cropped.
  * "-" writes them to stdout (a pipe to the GPU harness).  width/height size the author's analysis
  * buffers that his hooks in the macroblock decoder write unconditionally (curr_frm, curr_res:
@@ -46,9 +50,38 @@ static unsigned char ***alloc3(int h, int w, int c)
     return p;
 }
 
+void img2buf(imgpel **imgX, unsigned char *buf, int size_x, int size_y, int symbol_size_in_bytes, int crop_left,
+             int crop_right, int crop_top, int crop_bottom);          /* lib/JM/output.c:87 */
+
+static int img2buf_mode(char **a)
+{
+    const int sx = atoi(a[0]), sy = atoi(a[1]), cl = atoi(a[2]), cr = atoi(a[3]), ct = atoi(a[4]), cb = atoi(a[5]);
+    const size_t n = (size_t)sx * sy, on = (size_t)(sx - cl - cr) * (sy - ct - cb);
+    imgpel *data = (imgpel *)malloc(n * sizeof(imgpel));
+    imgpel **rows = (imgpel **)malloc((size_t)sy * sizeof(imgpel *));
+    unsigned char *out = (unsigned char *)malloc(n);
+    size_t got = 0, put = 0;
+    int i;
+    if (sx <= 0 || sy <= 0 || !data || !rows || !out) return 3;
+    while (got < n * sizeof(imgpel)) {
+        ssize_t r = read(0, (char *)data + got, n * sizeof(imgpel) - got);
+        if (r <= 0) return 4;
+        got += (size_t)r;
+    }
+    for (i = 0; i < sy; i++) rows[i] = data + (size_t)i * sx;          /* the layout of get_mem2Dpel, memalloc.c:26-39 */
+    img2buf(rows, out, sx, sy, 1, cl, cr, ct, cb);
+    while (put < on) {
+        ssize_t r = write(1, out + put, on - put);
+        if (r <= 0) return 5;
+        put += (size_t)r;
+    }
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     int w, h, mbs;
+    if (argc == 8 && strcmp(argv[1], "--img2buf") == 0) return img2buf_mode(argv + 2);
     if (argc < 5) {
         fprintf(stderr, "usage: %s stream.264 out.yuv|- width height\n", argv[0]);
         return 2;

@@ -463,3 +463,32 @@ uint32_t lvo_crc32(const uint8_t *p, uint64_t n)
     for (uint64_t i = 0; i < n; i++) c = tab[(c ^ p[i]) & 0xFF] ^ (c >> 8);
     return c ^ 0xFFFFFFFFU;
 }
+
+/* ---- decoder picture -> planar 8-bit I420 ----------------------------------------------------------------------- */
+/* img2buf, lib/JM/output.c:87-178.  On a little-endian host with sizeof(imgpel) == 2 > symbol_size_in_bytes == 1 the
+ * function takes the last branch (output.c:161-176): size = 1 and
+ *     memcpy(buf + (j - crop_left + (i - crop_top) * twidth), &imgX[i][j], 1)
+ * i.e. the first byte in memory of the short = its low byte. */
+void lvo_img2buf(const uint16_t *plane, int size_x, int size_y, int crop_left, int crop_right, int crop_top,
+                 int crop_bottom, uint8_t *buf)
+{
+    const int twidth = size_x - crop_left - crop_right;
+    for (int i = crop_top; i < size_y - crop_bottom; i++)
+        for (int j = crop_left; j < size_x - crop_right; j++)
+            buf[(j - crop_left) + (size_t)(i - crop_top) * twidth] = (uint8_t)(plane[(size_t)i * size_x + j] & 0xffu);
+}
+
+/* write_out_picture, lib/JM/output.c:362-453, for chroma_format_idc == 1 (4:2:0) and YUV output: the luma crop is
+ * SubWidthC/SubHeightC (= 2) times the SPS offsets (output.c:375-380), the chroma crop the offsets themselves
+ * (output.c:421-425); planes leave in the order Y (427-428), imgUV[0] (437-438), imgUV[1] (446-447). */
+void lvo_picture16_to_i420(const uint16_t *pic16, int size_x, int size_y, int crop_left, int crop_right, int crop_top,
+                           int crop_bottom, uint8_t *i420)
+{
+    const int w = size_x - crop_left - crop_right, h = size_y - crop_top - crop_bottom;
+    const int cx = size_x / 2, cy = size_y / 2;
+    const uint16_t *u16 = pic16 + (size_t)size_x * size_y, *v16 = u16 + (size_t)cx * cy;
+    lvo_img2buf(pic16, size_x, size_y, crop_left, crop_right, crop_top, crop_bottom, i420);
+    lvo_img2buf(u16, cx, cy, crop_left / 2, crop_right / 2, crop_top / 2, crop_bottom / 2, i420 + (size_t)w * h);
+    lvo_img2buf(v16, cx, cy, crop_left / 2, crop_right / 2, crop_top / 2, crop_bottom / 2,
+                i420 + (size_t)w * h + (size_t)(w / 2) * (h / 2));
+}

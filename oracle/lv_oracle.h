@@ -73,6 +73,19 @@ void lvo_yuy2_to_yv12(const uint8_t *in, uint8_t *out, int w, int h);    /* chro
 void lvo_yv12_to_yvu9(const uint8_t *in, uint8_t *out, int w, int h);    /* chroma point-sampled 2:1 both ways */
 void lvo_yv12_to_yuy2(const uint8_t *in, uint8_t *out, int w, int h);
 
+/* ---- the decoder's picture -> planar 8-bit I420 (lib/JM/output.c) --------------------------------------------
+ * lvo_img2buf: img2buf (output.c:87-178), the little-endian branch with symbol_size_in_bytes == 1 and
+ * imgpel == unsigned short (global.h:61): every sample keeps ONE byte of its little-endian short -- the low byte, no
+ * clipping -- and the crop rectangle is cut away.  Pinned against the reference's own compiled img2buf
+ * (oracle/_ref/jm_ldecod --img2buf, tests/test_oracle.py, tests/golden).
+ * lvo_picture16_to_i420: write_out_picture's plane order and crops for 4:2:0 (output.c:375-385, 427-451): Y with the
+ * luma crop, then U (imgUV[0]) and V (imgUV[1]) with half of it.  pic16 = Y16[size_x*size_y] U16 V16 (size_x/2 x
+ * size_y/2 each), each plane contiguous like get_mem2Dpel's (memalloc.c:26-39).  Crops in luma pixels (even). */
+void lvo_img2buf(const uint16_t *plane, int size_x, int size_y, int crop_left, int crop_right, int crop_top,
+                 int crop_bottom, uint8_t *buf);
+void lvo_picture16_to_i420(const uint16_t *pic16, int size_x, int size_y, int crop_left, int crop_right, int crop_top,
+                           int crop_bottom, uint8_t *i420);
+
 /* ---- object box from the mask (image.c:4818-4848) ----------------------------------------- */
 /* box[4] = {min_x, max_x, min_y, max_y} over mask==1 inside the window [x0..x1]x[y0..y1] (inclusive);
  * empty => {x1+1, x0-1, y1+1, y0-1} exactly as the reference initialises them. */

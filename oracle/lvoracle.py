@@ -51,6 +51,8 @@ def lib():
         L.lvo_object_box.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         for name in ("lvo_rgb24_to_yv12", "lvo_yvu9_to_yv12", "lvo_yuy2_to_yv12", "lvo_yv12_to_yvu9", "lvo_yv12_to_yuy2"):
             getattr(L, name).argtypes = [_u8p, _u8p, C.c_int, C.c_int]
+        L.lvo_img2buf.argtypes = [_u16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        L.lvo_picture16_to_i420.argtypes = [_u16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
         L.lvo_lowbias32.argtypes = [C.c_uint32]
         L.lvo_lowbias32.restype = C.c_uint32
         L.lvo_gen_uniform.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _u8p]
@@ -162,6 +164,34 @@ def convert_format(name, data, w, h):
     out = np.zeros(w * h // 8 * outb, dtype=np.uint8)
     getattr(lib(), "lvo_" + name)(_p(data), _p(out), w, h)
     return out
+
+
+def img2buf(plane16, size_x, size_y, cl, cr, ct, cb):
+    """lib/JM/output.c:87-178 (1-byte symbols from unsigned-short samples): low byte + crop."""
+    plane16 = np.ascontiguousarray(plane16, dtype=np.uint16).ravel()
+    out = np.empty((size_x - cl - cr) * (size_y - ct - cb), dtype=np.uint8)
+    lib().lvo_img2buf(_p(plane16, _u16p), size_x, size_y, cl, cr, ct, cb, _p(out))
+    return out
+
+
+def picture16_to_i420(pic16, size_x, size_y, cl, cr, ct, cb):
+    """write_out_picture's Y, U, V order and crops (output.c:362-453) over one decoder picture of 16-bit planes."""
+    pic16 = np.ascontiguousarray(pic16, dtype=np.uint16).ravel()
+    w, h = size_x - cl - cr, size_y - ct - cb
+    out = np.empty(w * h * 3 // 2, dtype=np.uint8)
+    lib().lvo_picture16_to_i420(_p(pic16, _u16p), size_x, size_y, cl, cr, ct, cb, _p(out))
+    return out
+
+
+def jm_img2buf(plane16, size_x, size_y, cl, cr, ct, cb):
+    """The reference's OWN compiled img2buf (oracle/_ref/jm_ldecod --img2buf), or None when the binary is absent."""
+    exe = os.path.join(_HERE, "_ref", "jm_ldecod")
+    if not os.path.exists(exe):
+        return None
+    data = np.ascontiguousarray(plane16, dtype=np.uint16).tobytes()
+    r = subprocess.run([exe, "--img2buf", str(size_x), str(size_y), str(cl), str(cr), str(ct), str(cb)], input=data,
+                       capture_output=True, check=True)
+    return np.frombuffer(r.stdout, dtype=np.uint8)
 
 
 def lowbias32(x):

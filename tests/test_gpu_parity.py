@@ -754,3 +754,60 @@ def test_legacy_entries_from_several_threads_and_registered_buffers(lv, orc, tor
         finally:
             torch.cuda.set_device(0)
         assert np.array_equal(dst, dst2) and np.array_equal(dst, ref["bgr"][3 * px:6 * px])
+
+
+@pytest.mark.parametrize("sx,sy,cl,ct,w,h", [(1920, 1088, 0, 0, 1920, 1080), (384, 304, 16, 8, 352, 288), (64, 48, 0, 0, 64, 48),
+                                             (48, 32, 4, 2, 40, 24), (1296, 736, 8, 6, 1280, 720), (96, 64, 32, 16, 64, 48)])
+def test_narrow_pictures_matches_img2buf(lv, orc, torch_cuda, sx, sy, cl, ct, w, h):
+    """lv_narrow_pictures = the reference's img2buf + write_out_picture (lib/JM/output.c:87-178, 362-453) on the device:
+    vector kernel (16-byte aligned crops) and the generic one, 10-bit and full 16-bit content (upper byte dropped, not
+    clipped), several pictures per launch; then straight into the fused step."""
+    torch = torch_cuda
+    n = 3
+    rng = np.random.default_rng(sx + w)
+    samples = sx * sy * 3 // 2
+    pics = rng.integers(0, 65536, (n, samples), dtype=np.uint16)
+    pics[1] &= 0x3ff
+    want = np.stack([orc.picture16_to_i420(pics[i], sx, sy, cl, sx - cl - w, ct, sy - ct - h) for i in range(n)])
+    ctx = lv.Context(w, h)
+    d_pic = torch.from_numpy(pics.view(np.int16).reshape(-1)).cuda()
+    d_out = torch.zeros(n * ctx.frame_bytes, dtype=torch.uint8, device="cuda")
+    ctx.narrow_pictures(d_pic, n, sx, sy, cl, ct, d_out)
+    assert np.array_equal(d_out.cpu().numpy(), want.reshape(-1)), (sx, sy, cl, ct, w, h)
+    if w % 16 == 0:
+        out = ctx.alloc_outputs(n)
+        ctx.convert_diff_batch(d_out, 1, n, out)
+        ref = orc.convert_diff_batch(want.reshape(1, n, -1), np.zeros((1, w * h), np.uint8), 1, n, w, h, 20, 0, want_mask=False)
+        assert np.array_equal(out["bgr"].cpu().numpy(), ref["bgr"])
+    from livevideo_b200.capi import LiveVideoError
+    with pytest.raises(LiveVideoError):
+        ctx.narrow_pictures(d_pic, n, sx, sy, cl + 1, ct, d_out)        # odd crop
+    with pytest.raises(LiveVideoError):
+        ctx.narrow_pictures(d_pic, n, sx, sy, sx - w + 2, ct, d_out)    # rectangle leaves the picture
+    ctx.close()
+
+
+def test_step_host_pictures_equals_narrow_then_step(lv, orc, torch_cuda):
+    """lv_step_host_pictures: raw decoder pictures in host memory -> (device) img2buf/write_out_picture -> fused step,
+    chunked; equals the oracle's picture16_to_i420 followed by the fused oracle step, state carried across two calls."""
+    sx, sy, cl, ct, w, h = 384, 304, 16, 8, 352, 288
+    ns, nf = 2, 5
+    rng = np.random.default_rng(21)
+    samples = sx * sy * 3 // 2
+    ctx = lv.Context(w, h, ns)
+    prev = np.zeros((ns, w * h), np.uint8)
+    import os
+    os.environ["LV_HOST_CHUNK_MB"] = "1"           # several chunks per call (read once per process: harmless if already set)
+    for call in range(2):
+        pics = (rng.integers(0, 256, (ns, nf, samples), dtype=np.uint16) | (rng.integers(0, 4, (ns, nf, samples), dtype=np.uint16) << 8))
+        frames = np.stack([[orc.picture16_to_i420(pics[s, t], sx, sy, cl, sx - cl - w, ct, sy - ct - h) for t in range(nf)]
+                           for s in range(ns)])
+        ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, 20, 0, want_mask=False)
+        n = ns * nf
+        bgr, cnt = np.zeros(n * ctx.bgr_bytes, np.uint8), np.zeros(n * ctx.mbs, np.uint16)
+        mp, sm = np.zeros(n * ctx.mbs, np.uint8), np.zeros(2 * n, np.uint32)
+        ctx.step_host_pictures(np.ascontiguousarray(pics).reshape(-1), sx, sy, cl, ct, ns, nf, bgr=bgr, mb_count=cnt, mb_map=mp,
+                               summary=sm)
+        assert np.array_equal(bgr, ref["bgr"]) and np.array_equal(cnt, ref["mb_count"])
+        assert np.array_equal(mp, ref["mb_map"]) and np.array_equal(sm.reshape(-1, 2), ref["summary"])
+    ctx.close()

@@ -257,3 +257,56 @@ def test_other_converters_known_values(orc):
     src = yuy2.reshape(h, w // 2, 4)
     assert np.array_equal(back[:, :, 0::2], src[:, :, 0::2])
     assert np.array_equal(back[0::2, :, 1::2], src[1::2, :, 1::2]) and np.array_equal(back[1::2, :, 1::2], src[1::2, :, 1::2])
+
+
+# ---- the decoder picture -> I420 step (img2buf / write_out_picture, lib/JM/output.c) ------------------------------
+def _plane16(n, seed, mask):
+    i = np.arange(n, dtype=np.uint64)
+    x = (i + seed) & 0xffffffff
+    x ^= x >> 16
+    x = (x * 0x7feb352d) & 0xffffffff
+    x ^= x >> 15
+    x = (x * 0x846ca68b) & 0xffffffff
+    x ^= x >> 16
+    return (x & mask).astype(np.uint16)
+
+
+def test_img2buf_matches_golden_from_the_reference_code(orc):
+    """tests/golden/img2buf.json was produced by the reference's own compiled img2buf (make_img2buf_golden.py)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "img2buf.json")) as f:
+        g = json.load(f)
+    assert len(g["cases"]) >= 8
+    for c in g["cases"]:
+        sx, sy, (cl, cr, ct, cb) = c["size_x"], c["size_y"], c["crop"]
+        p = _plane16(sx * sy, c["seed"], c["mask"])
+        out = orc.img2buf(p, sx, sy, cl, cr, ct, cb)
+        assert out.size == c["bytes"] and [int(v) for v in out[:8]] == c["first8"]
+        assert hashlib.sha256(out.tobytes()).hexdigest() == c["sha256"], c
+        # the semantics in one line: low byte of the sample, crop rectangle cut away
+        want = (p.reshape(sy, sx)[ct:sy - cb, cl:sx - cr] & 0xff).astype(np.uint8).ravel()
+        assert np.array_equal(out, want)
+
+
+def test_img2buf_against_the_live_reference_code(orc):
+    """Where oracle/_ref/jm_ldecod exists (this container), compare with the reference's function directly."""
+    rng = np.random.default_rng(3)
+    if orc.jm_img2buf(np.zeros(4, np.uint16), 2, 2, 0, 0, 0, 0) is None:
+        pytest.skip("oracle/_ref/jm_ldecod not built here")
+    for (sx, sy, cl, cr, ct, cb) in [(32, 16, 0, 0, 0, 0), (40, 24, 8, 4, 2, 6), (1920, 1088, 0, 0, 0, 8), (18, 10, 2, 2, 2, 2)]:
+        p = rng.integers(0, 65536, sx * sy, dtype=np.uint16)
+        assert np.array_equal(orc.img2buf(p, sx, sy, cl, cr, ct, cb), orc.jm_img2buf(p, sx, sy, cl, cr, ct, cb))
+
+
+def test_picture16_to_i420_plane_order_and_half_crop(orc):
+    """write_out_picture (output.c:362-453): Y with the luma crop, then imgUV[0], imgUV[1] with half of it."""
+    sx, sy, cl, cr, ct, cb = 48, 32, 4, 12, 2, 6
+    rng = np.random.default_rng(4)
+    pic = rng.integers(0, 1024, sx * sy * 3 // 2, dtype=np.uint16)
+    out = orc.picture16_to_i420(pic, sx, sy, cl, cr, ct, cb)
+    w, h = sx - cl - cr, sy - ct - cb
+    y = orc.img2buf(pic[:sx * sy], sx, sy, cl, cr, ct, cb)
+    u = orc.img2buf(pic[sx * sy:sx * sy * 5 // 4], sx // 2, sy // 2, cl // 2, cr // 2, ct // 2, cb // 2)
+    v = orc.img2buf(pic[sx * sy * 5 // 4:], sx // 2, sy // 2, cl // 2, cr // 2, ct // 2, cb // 2)
+    assert out.size == w * h * 3 // 2 and np.array_equal(out, np.concatenate([y, u, v]))

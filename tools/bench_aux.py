@@ -71,6 +71,11 @@ def main():
         boxes = torch.empty(4 * n, dtype=torch.int32, device="cuda")
         row("object_box_batch (byte mask)", timeit(lambda: L.lv_object_box_batch(ctx._h, mb.data_ptr(), 0, n, 0, w - 1, 0, h - 1, boxes.data_ptr(), st)), 1.0)
         row("object_box_batch (bit mask)", timeit(lambda: L.lv_object_box_batch(ctx._h, mbits.data_ptr(), 1, n, 0, w - 1, 0, h - 1, boxes.data_ptr(), st)), 0.125)
+    # decoder pictures (16-bit planes, 1920x1088 coded for 1080 lines) -> tight I420
+    sx, sy = (w + 15) // 16 * 16, (h + 15) // 16 * 16
+    pic = torch.randint(0, 1024, (n * (sx * sy * 3 // 2),), dtype=torch.int16, device="cuda")
+    row("narrow_pictures (img2buf on device)", timeit(lambda: ctx.narrow_pictures(pic, n, sx, sy, 0, 0, o420)), 4.5,
+        note=f"{sx}x{sy} 16-bit 4:2:0 in (3 B/px) + 1.5 B/px out")
     names = {1: "RGB24_to_YV12", 2: "YVU9_to_YV12", 3: "YUY2_to_YV12", 4: "YV12_to_YVU9", 5: "YV12_to_YUY2"}
     for kind in range(1, 6):
         ib, ob = L.lv_format_bytes(kind, w, h, 0), L.lv_format_bytes(kind, w, h, 1)
