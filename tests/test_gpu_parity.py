@@ -811,3 +811,26 @@ def test_step_host_pictures_equals_narrow_then_step(lv, orc, torch_cuda):
         assert np.array_equal(bgr, ref["bgr"]) and np.array_equal(cnt, ref["mb_count"])
         assert np.array_equal(mp, ref["mb_map"]) and np.array_equal(sm.reshape(-1, 2), ref["summary"])
     ctx.close()
+
+
+def test_more_than_65535_frames_per_call(lv, orc, torch_cuda):
+    """gridDim.z is limited to 65535: long batches are cut into launch groups (by streams for the fused step, by frames
+    for the single-purpose entries) without changing any result -- 3 streams x 30 000 tiny frames = 90 000 frames."""
+    torch = torch_cuda
+    w, h, ns, nf = 16, 2, 3, 30000
+    rng = np.random.default_rng(65535)
+    frames = rng.integers(0, 256, (ns, nf, w * h * 3 // 2), dtype=np.uint8)
+    frames[:, 1::2, :w * h] = frames[:, 0:-1:2, :w * h]              # every other frame repeats its predecessor's luma
+    prev = np.zeros((ns, w * h), np.uint8)
+    ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, 20, 0, want_mask=False, n_threads=8)
+    got = run_fused(lv, torch, frames, ns, nf, w, h, 20, 0, masks=False)
+    assert np.array_equal(got["bgr"], ref["bgr"])
+    assert np.array_equal(got["mb_count"], ref["mb_count"]) and np.array_equal(got["mb_map"], ref["mb_map"])
+    assert np.array_equal(got["summary"], ref["summary"]) and np.array_equal(got["state"], prev)
+    ctx = lv.Context(w, h)
+    n = ns * nf
+    d_in = torch.from_numpy(frames.reshape(-1)).cuda()
+    d_bgr = torch.empty(n * ctx.bgr_bytes, dtype=torch.uint8, device="cuda")
+    ctx.convert_batch(d_in, n, d_bgr)
+    assert np.array_equal(d_bgr.cpu().numpy(), ref["bgr"])
+    ctx.close()
