@@ -257,7 +257,9 @@ LV_API int lv_device_sm_count(const lv_ctx *ctx);
  *   lv_exchange_collect(step, d_table, stream)   d_table = world x slot_words u32 (row r = rank r), or NULL to retire
  *                          the step unread; every step must be collected, in order, within `depth` steps, and the
  *                          caller must not launch the fused kernel of step+depth before this collect has finished
- *   lv_exchange_error      0, or which wait gave up after 4 s (1 publish / 2 collect): a wait never spins forever */
+ *   lv_exchange_error      0, or which wait gave up after 4 s (1 publish / 2 collect): a wait never spins forever
+ *   lv_exchange_destroy    only after every rank has collected the last step it will publish (a barrier of the
+ *                          launcher): peers store into this rank's buffer until then */
 typedef struct lv_exchange lv_exchange;
 LV_API size_t lv_exchange_bytes(int world, int depth, int slot_words);
 LV_API int lv_exchange_create(int device, int rank, int world, int depth, int slot_words, lv_exchange **out);
