@@ -124,6 +124,14 @@ LV_API int lv_convert_diff_batch(lv_ctx *ctx, const uint8_t *d_i420, int first_s
                                  uint8_t *d_mask_bytes, uint16_t *d_mb_count, uint8_t *d_mb_map,
                                  uint32_t *d_summary, void *cuda_stream);
 
+/* Same, with flags.  LV_STEP_SUMMARY_PREZEROED: d_summary already holds zeros (the blocks of the fused kernel add into
+ * it; the plain entry issues a memset in front of the launch). */
+#define LV_STEP_SUMMARY_PREZEROED 1
+LV_API int lv_convert_diff_batch_ex(lv_ctx *ctx, const uint8_t *d_i420, int first_stream, int n_streams,
+                                    int n_frames, uint8_t *d_bgr, uint16_t *d_mask_bits, uint8_t *d_mask_bytes,
+                                    uint16_t *d_mb_count, uint8_t *d_mb_map, uint32_t *d_summary, void *cuda_stream,
+                                    int flags);
+
 /* Conversion only (K2) and difference only (K3) over n frames; same layouts as above.
  * lv_diff_batch: frame i of d_cur_y (w*h bytes each) against frame i of d_ref_y. */
 LV_API int lv_convert_batch(lv_ctx *ctx, const uint8_t *d_i420, int n_frames, uint8_t *d_bgr,
@@ -243,20 +251,27 @@ LV_API int lv_device_sm_count(const lv_ctx *ctx);
 /* ---- peer-memory exchange of the change summaries (one process per GPU; csrc/lv_exchange.cu) ------------------------
  * The only exchange of the sharded path: every rank wants every rank's {changed_px, changed_mbs} per
  * (stream, frame).  Instead of a per-step library all-gather, each rank pushes its block into every peer's table with
- * NVLink stores from one tiny kernel behind the fused kernel, followed by a sequence flag; a collect waits on local
- * flags only.  Ranks never rendezvous; a rank blocks only when it is a whole ring (`depth` steps) ahead of a peer.
+ * NVLink stores -- every 8-byte store carries one word and its own sequence number, so there is no flag and no fence --
+ * and a collect spins on local memory only.  Ranks never rendezvous; a rank waits only when it is about half a ring
+ * (`depth` / 2 steps) ahead of a peer.
  *
- *   lv_exchange_create     allocates this rank's buffer (ring of `depth` tables of world x slot_words u32 + flags)
+ *   lv_exchange_create     allocates this rank's buffer (ring of `depth` tables of world x slot_words words)
  *   lv_exchange_handle     64-byte CUDA IPC handle of it; hand the handles of all ranks to lv_exchange_connect
  *                          (any transport: torch.distributed, MPI, a file) or pass already-mapped pointers to
  *                          lv_exchange_connect_ptrs (one process driving several ranks, VMM / symmetric allocations)
- *   lv_exchange_local_block(step)  device pointer to hand to lv_convert_diff_batch as d_summary for that step: the
- *                          fused kernel writes this rank's block in place, there is no staging copy
- *   lv_exchange_publish(step, n_words, d_local_copy, stream)   after the fused kernel of `step` in stream order; steps
- *                          in order; d_local_copy (optional) also receives this rank's n_words
- *   lv_exchange_collect(step, d_table, stream)   d_table = world x slot_words u32 (row r = rank r), or NULL to retire
- *                          the step unread; every step must be collected, in order, within `depth` steps, and the
- *                          caller must not launch the fused kernel of step+depth before this collect has finished
+ *   lv_exchange_step       the whole sharded step: the fused kernel accumulates into a ring row owned by the exchange;
+ *                          behind an event, on the exchange's own side stream, one small kernel pushes that row to
+ *                          every peer (and copies it to d_summary, optional) and another collects an older step.  The
+ *                          caller's stream receives the two launches of the single-GPU step plus one event record.
+ *   lv_exchange_result     table of `step` (world rows of slot_words u32, device memory owned by the exchange, valid
+ *                          until `depth` further steps have been issued); blocks the host until every rank's block of
+ *                          that step has arrived (every rank must have issued that step); afterwards d_summary of
+ *                          every step up to `step` is filled too
+ *   lv_exchange_flush      nothing to do in this design (every push is on its way when lv_exchange_step returns);
+ *                          kept so that callers need not know
+ *   lv_exchange_publish / lv_exchange_collect   the two halves on their own (not to be mixed with lv_exchange_step):
+ *                          publish(step, d_block, n_words) in order, once per step; collect(step, d_table) in order,
+ *                          within `depth` steps; d_table = world x slot_words u32 or NULL to retire the step unread
  *   lv_exchange_error      0, or which wait gave up after 4 s (1 publish / 2 collect): a wait never spins forever
  *   lv_exchange_destroy    only after every rank has collected the last step it will publish (a barrier of the
  *                          launcher): peers store into this rank's buffer until then */
@@ -268,20 +283,15 @@ LV_API void *lv_exchange_buffer(lv_exchange *x);
 LV_API int lv_exchange_handle(lv_exchange *x, unsigned char *handle64);
 LV_API int lv_exchange_connect(lv_exchange *x, const unsigned char *handles);
 LV_API int lv_exchange_connect_ptrs(lv_exchange *x, void *const *peer_buffers);
-LV_API uint32_t *lv_exchange_local_block(lv_exchange *x, uint64_t step);
-LV_API int lv_exchange_publish(lv_exchange *x, uint64_t step, int n_words, uint32_t *d_local_copy, void *cuda_stream);
-LV_API int lv_exchange_collect(lv_exchange *x, uint64_t step, uint32_t *d_table, void *cuda_stream);
-LV_API int lv_exchange_error(lv_exchange *x);
-/* The whole sharded step in one call: lv_convert_diff_batch with its summary written straight into this rank's block of
- * the ring, the push to every peer and the collect of an earlier step on the exchange's own side stream.  d_summary
- * (optional) still receives this rank's block.  *step = the step's number; lv_exchange_result(step) blocks the host
- * until every rank's block of that step has arrived and returns the table (world rows of slot_words u32, device memory
- * owned by the exchange, valid until `depth` further steps have been issued).  Do not mix with manual publish/collect. */
 LV_API int lv_exchange_step(lv_exchange *x, lv_ctx *ctx, const uint8_t *d_i420, int first_stream, int n_streams,
                             int n_frames, uint8_t *d_bgr, uint16_t *d_mask_bits, uint8_t *d_mask_bytes,
                             uint16_t *d_mb_count, uint8_t *d_mb_map, uint32_t *d_summary, void *cuda_stream,
                             uint64_t *step);
+LV_API int lv_exchange_flush(lv_exchange *x);
 LV_API int lv_exchange_result(lv_exchange *x, uint64_t step, const uint32_t **d_table);
+LV_API int lv_exchange_publish(lv_exchange *x, uint64_t step, const uint32_t *d_block, int n_words, void *cuda_stream);
+LV_API int lv_exchange_collect(lv_exchange *x, uint64_t step, uint32_t *d_table, void *cuda_stream);
+LV_API int lv_exchange_error(lv_exchange *x);
 LV_API const char *lv_exchange_last_error(void);
 
 #ifdef __cplusplus

@@ -34,6 +34,7 @@ SYMBOLS = {
     "lv_get_prev_luma": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
     "lv_reset_prev_luma": (C.c_int, [_vp, _vp]),
     "lv_convert_diff_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lv_convert_diff_batch_ex": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "lv_convert_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "lv_diff_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lv_write_bks": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
@@ -69,12 +70,12 @@ SYMBOLS = {
     "lv_exchange_handle": (C.c_int, [_vp, _vp]),
     "lv_exchange_connect": (C.c_int, [_vp, _vp]),
     "lv_exchange_connect_ptrs": (C.c_int, [_vp, C.POINTER(_vp)]),
-    "lv_exchange_local_block": (_vp, [_vp, C.c_uint64]),
-    "lv_exchange_publish": (C.c_int, [_vp, C.c_uint64, C.c_int, _vp, _vp]),
+    "lv_exchange_publish": (C.c_int, [_vp, C.c_uint64, _vp, C.c_int, _vp]),
     "lv_exchange_collect": (C.c_int, [_vp, C.c_uint64, _vp, _vp]),
     "lv_exchange_error": (C.c_int, [_vp]),
     "lv_exchange_step": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    C.POINTER(C.c_uint64)]),
+    "lv_exchange_flush": (C.c_int, [_vp]),
     "lv_exchange_result": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
     "lv_exchange_last_error": (C.c_char_p, []),
     "lv_set_kernel_variant": (C.c_int, [C.c_int]),

@@ -266,13 +266,22 @@ int lv_convert_diff_batch(lv_ctx *c, const uint8_t *d_i420, int first_stream, in
                           uint8_t *d_bgr, uint16_t *d_mask_bits, uint8_t *d_mask_bytes, uint16_t *d_mb_count,
                           uint8_t *d_mb_map, uint32_t *d_summary, void *cuda_stream)
 {
+    return lv_convert_diff_batch_ex(c, d_i420, first_stream, n_streams, n_frames, d_bgr, d_mask_bits, d_mask_bytes, d_mb_count,
+                                    d_mb_map, d_summary, cuda_stream, 0);
+}
+
+int lv_convert_diff_batch_ex(lv_ctx *c, const uint8_t *d_i420, int first_stream, int n_streams, int n_frames,
+                             uint8_t *d_bgr, uint16_t *d_mask_bits, uint8_t *d_mask_bytes, uint16_t *d_mb_count,
+                             uint8_t *d_mb_map, uint32_t *d_summary, void *cuda_stream, int flags)
+{
     if (!c || !d_i420) return LV_E_ARG;
     if (n_streams < 0 || n_frames < 0 || first_stream < 0 || first_stream + n_streams > c->max_streams) return LV_E_ARG;
     if (!geom_fast(c->g.w, c->g.h)) return LV_E_SIZE;
     if (n_streams == 0 || n_frames == 0) return LV_OK;
     DeviceGuard guard(c->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (d_summary) LV_CUDA(cudaMemsetAsync(d_summary, 0, sizeof(uint32_t) * 2 * (size_t)n_streams * n_frames, st));
+    if (d_summary && !(flags & LV_STEP_SUMMARY_PREZEROED))
+        LV_CUDA(cudaMemsetAsync(d_summary, 0, sizeof(uint32_t) * 2 * (size_t)n_streams * n_frames, st));
     lv::StepArgs a{};
     a.g = c->g;
     a.i420 = d_i420;

@@ -3,23 +3,32 @@
 // The path shards by stream ID with no data-path collective; the one exchange it has is the few
 // hundred bytes of {changed_px, changed_mbs} per step that every rank wants from every other rank.  A library
 // all-gather of that size is pure latency (an 8-rank NCCL all-gather costs more than the whole 114 us kernel) and
-// its kernels handshake across all GPUs every step.  Here each rank instead PUSHES its block straight into every
-// peer's table with NVLink stores from one tiny kernel behind the fused kernel, followed by a sequence flag:
+// its kernels rendezvous across all GPUs every step.  Here each rank PUSHES its block straight into every peer's table
+// with NVLink stores, and nothing on the step ever waits for a round trip:
 //
 //   symmetric buffer (one per rank, same layout, peers map each other's through CUDA IPC or any shared mapping)
-//     data [depth][world][slot_words]   u32   table of step k lives in ring slot k % depth; row r is rank r's block
-//     flag [depth][world]               u32   flag[slot][r] == k+1  <=>  rank r's block of step k has landed here
+//     data [depth][world][slot_words]  u64   word i of rank r's block of step k lives in ring slot k % depth as
+//                                            {value (low 32 bits), k+1 (high 32 bits)}: ONE 8-byte store carries the
+//                                            word and its own sequence number, so the receiver needs no flag behind a
+//                                            fence -- a word has arrived when its upper half says k+1
 //     ack  [world]                      u32   ack[r] == number of steps rank r has collected (retired)
-//     err                               u32   set when a wait gave up (never spins forever: a hung GPU is worse)
+//     err                               u32   set when a wait gave up (a wait never spins forever: a hung GPU is worse)
 //
-//   publish(k): wait until every rank has retired step k-depth (ack >= k-depth+1; free in steady state), copy the
-//               local block (the fused kernel wrote it directly into data[slot][rank] of the LOCAL buffer, so there is
-//               no staging copy) to data[slot][rank] of every peer, fence, then store flag[slot][rank] = k+1 at every
-//               peer (and locally).
-//   collect(k): wait for flag[slot][r] == k+1 for all r (local memory, peers wrote it), copy data[slot] to the
-//               caller's table, then store ack[rank] = k+1 at every peer (and locally).
+//   publish(k): wait (local reads) until every rank has retired step k-depth, then store the block, fire and forget.
+//   collect(k): spin on LOCAL memory until every word of ring slot k % depth carries k+1, copy the values out, then
+//               store ack = k+1 into every peer (the loads have returned by then; nothing to fence).
 //
-// No rank ever waits for a peer unless it is a whole ring (depth steps) ahead: there is no per-step rendezvous.
+//   lv_exchange_step: the fused kernel of step k accumulates into row k % depth of a ring owned by the exchange; behind
+//     an event, on the exchange's own side stream, one small kernel pushes that row (and copies it to the caller's
+//     d_summary) and another collects step k-lag.  The caller's stream gets the two launches of the single-GPU step
+//     plus one event record; it waits for the side stream only if the push of step k-depth has not finished when step
+//     k is issued (checked on the host: practically never).
+//
+// Measured alternatives (profiles/README.md, N = 2, us per step over the single-GPU 116.3): this design with flag +
+// __threadfence_system() instead of sequence-numbered words +1.4; the same pushes from a kernel IN the caller's stream
+// (in place of the memset) +5.2 with or without fences -- a kernel that stores to a peer ends only after the NVLink
+// write acknowledgements; letting block 0 of the fused kernel carry the exchange slowed the fused kernel's own code
+// by 10-14 % (even as a never-taken noinline call); NCCL all-gather started asynchronously +4.7.
 #include "../../include/livevideo.h"
 
 #include <cuda_runtime.h>
@@ -30,7 +39,7 @@
 
 namespace {
 
-constexpr int kMaxWorld = 32;               // one warp per peer in k_publish (<= 1024 threads)
+constexpr int kMaxWorld = 32;
 constexpr unsigned long long kSpinLimitNs = 4000000000ull;   // a wait gives up after 4 s and raises err
 
 thread_local char x_err[256] = "";
@@ -48,26 +57,35 @@ int x_fail(cudaError_t e, const char *what)
 
 struct Layout {
     int world, depth, slot_words;
-    __host__ __device__ size_t data_words() const { return (size_t)depth * world * slot_words; }
-    __host__ __device__ size_t flag_off() const { return data_words(); }                        // in u32 words
-    __host__ __device__ size_t ack_off() const { return flag_off() + (size_t)depth * world; }
-    __host__ __device__ size_t err_off() const { return ack_off() + (size_t)world; }
-    __host__ __device__ size_t words() const { return (err_off() + 1 + 3) & ~(size_t)3; }
+    __host__ __device__ size_t data_words64() const { return (size_t)depth * world * slot_words; }
+    __host__ __device__ size_t ack_off32() const { return 2 * data_words64(); }                  // in u32 words
+    __host__ __device__ size_t err_off32() const { return ack_off32() + (size_t)world; }
+    __host__ __device__ size_t bytes() const { return ((err_off32() + 1) * 4 + 15) & ~(size_t)15; }
 };
 
 struct Peers {
-    uint32_t *p[kMaxWorld];
+    unsigned long long *p[kMaxWorld];
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+__device__ __forceinline__ unsigned long long ld_volatile64(const unsigned long long *p)
 {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+__device__ __forceinline__ uint32_t ld_volatile32(const uint32_t *p)
 {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_volatile32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long now_ns()
 {
@@ -75,84 +93,96 @@ __device__ __forceinline__ unsigned long long now_ns()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-
-// spin until *p (local memory, written by a peer) is >= want (sequence numbers only grow); false on timeout
-__device__ bool wait_ge(const uint32_t *p, uint32_t want)
+__device__ __forceinline__ uint32_t *ack_of(unsigned long long *buf, const Layout &L)
 {
-    if ((int32_t)(ld_acquire_sys(p) - want) >= 0) return true;
-    const unsigned long long t0 = now_ns();
-    for (;;) {
-        if ((int32_t)(ld_acquire_sys(p) - want) >= 0) return true;
-        __nanosleep(200);
-        if (now_ns() - t0 > kSpinLimitNs) return false;
-    }
+    return reinterpret_cast<uint32_t *>(buf) + L.ack_off32();
+}
+__device__ __forceinline__ uint32_t *err_of(unsigned long long *buf, const Layout &L)
+{
+    return reinterpret_cast<uint32_t *>(buf) + L.err_off32();
 }
 
-// one block of 32 * world threads (warp r serves peer r); n_words <= slot_words
-__global__ void k_publish(Peers peers, Layout L, int rank, uint32_t step, int n_words, uint32_t *local_copy)
+// Whole block.  Store this rank's block of `step` (n_words words at src, zero beyond, slot_words in all) into row `rank`
+// of ring slot step % depth of EVERY rank's table, each word with its sequence number; warp v serves ranks v, v+nwarps...
+__device__ void publish_block(const Peers &peers, const Layout &L, int rank, uint32_t step, const uint32_t *src, int n_words,
+                              uint32_t *local_copy, int *ok)
 {
-    uint32_t *local = peers.p[rank];
+    unsigned long long *local = peers.p[rank];
     const int slot = (int)(step % (uint32_t)L.depth);
-    const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __shared__ int ok;
-    if (threadIdx.x == 0) ok = 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) *ok = 1;
     __syncthreads();
-    // flow control: rank r must have retired the step that last used this ring slot
+    // flow control: every rank must have retired the step that last used this ring slot (local reads; free in steady state)
     if (step >= (uint32_t)L.depth && lane == 0) {
-        if (!wait_ge(local + L.ack_off() + r, step - (uint32_t)L.depth + 1u)) ok = 0;
+        const uint32_t want = step - (uint32_t)L.depth + 1u;
+        for (int r = warp; r < L.world; r += nwarps) {
+            const uint32_t *a = ack_of(local, L) + r;
+            if ((int32_t)(ld_volatile32(a) - want) >= 0) continue;
+            const unsigned long long t0 = now_ns();
+            while ((int32_t)(ld_volatile32(a) - want) < 0) {
+                __nanosleep(200);
+                if (now_ns() - t0 > kSpinLimitNs) { *ok = 0; break; }
+            }
+        }
     }
     __syncthreads();
-    if (!ok) {
-        if (threadIdx.x == 0) atomicExch(local + L.err_off(), 1u);
+    if (!*ok) {
+        if (threadIdx.x == 0) atomicExch(err_of(local, L), 1u);
         return;
     }
     const size_t row = ((size_t)slot * L.world + rank) * L.slot_words;
-    if (r != rank) {
-        const uint32_t *src = local + row;
-        uint32_t *dst = peers.p[r] + row;
-        if (((n_words | L.slot_words) & 3) == 0) {
-            for (int i = lane; i < n_words / 4; i += 32)
-                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
-        } else {
-            for (int i = lane; i < n_words; i += 32) dst[i] = src[i];
-        }
-    } else if (local_copy) {      // the caller's own summary buffer keeps its usual content
-        for (int i = lane; i < n_words; i += 32) local_copy[i] = local[row + i];
+    const unsigned long long seq = (unsigned long long)(step + 1u) << 32;
+    for (int r = warp; r < L.world; r += nwarps) {
+        unsigned long long *dst = peers.p[r] + row;
+        for (int i = lane; i < L.slot_words; i += 32) st_volatile64(dst + i, seq | (i < n_words ? src[i] : 0u));
+        if (r == rank && local_copy && local_copy != src)       // the caller's own summary buffer gets its usual content
+            for (int i = lane; i < n_words; i += 32) local_copy[i] = src[i];
     }
-    __threadfence_system();
-    __syncwarp();
-    if (lane == 0) st_release_sys(peers.p[r] + L.flag_off() + (size_t)slot * L.world + rank, step + 1u);
 }
 
-// one block of 256 threads; out = world rows of slot_words
-__global__ void k_collect(Peers peers, Layout L, int rank, uint32_t step, uint32_t *out)
+// Whole block.  Wait until every word of ring slot step % depth carries step+1, copy the values to `out` (world x slot_words
+// u32, may be NULL), then retire the step at every rank.
+__device__ void collect_block(const Peers &peers, const Layout &L, int rank, uint32_t step, uint32_t *out, int *ok)
 {
-    uint32_t *local = peers.p[rank];
+    unsigned long long *local = peers.p[rank];
     const int slot = (int)(step % (uint32_t)L.depth);
-    __shared__ int ok;
-    if (threadIdx.x == 0) ok = 1;
+    if (threadIdx.x == 0) *ok = 1;
     __syncthreads();
-    if (threadIdx.x < L.world) {
-        if (!wait_ge(local + L.flag_off() + (size_t)slot * L.world + threadIdx.x, step + 1u)) ok = 0;
+    const size_t n = (size_t)L.world * L.slot_words;
+    const unsigned long long *src = local + (size_t)slot * n;
+    const uint32_t want = step + 1u;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+        unsigned long long v = ld_volatile64(src + i);
+        if ((uint32_t)(v >> 32) != want) {
+            const unsigned long long t0 = now_ns();
+            do {
+                __nanosleep(200);
+                v = ld_volatile64(src + i);
+                if (now_ns() - t0 > kSpinLimitNs) { *ok = 0; break; }
+            } while ((uint32_t)(v >> 32) != want);
+        }
+        if (out) out[i] = (uint32_t)v;
     }
     __syncthreads();
-    if (!ok) {
-        if (threadIdx.x == 0) atomicExch(local + L.err_off(), 2u);
+    if (!*ok) {
+        if (threadIdx.x == 0) atomicExch(err_of(local, L), 2u);
         return;
     }
-    const size_t n = (size_t)L.world * L.slot_words;
-    const uint32_t *src = local + (size_t)slot * n;
-    if (out) {
-        if ((L.slot_words & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-            for (size_t i = threadIdx.x; i < n / 4; i += blockDim.x)
-                reinterpret_cast<uint4 *>(out)[i] = __ldcv(reinterpret_cast<const uint4 *>(src) + i);
-        } else {
-            for (size_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = __ldcv(src + i);
-        }
-    }
-    __syncthreads();
-    // retire: the slot may be overwritten once every rank has said so
-    if (threadIdx.x < L.world) st_release_sys(peers.p[threadIdx.x] + L.ack_off() + rank, step + 1u);
+    // retire: the slot may be overwritten once every rank has said so (all loads above have returned)
+    for (int r = threadIdx.x; r < L.world; r += blockDim.x) st_volatile32(ack_of(peers.p[r], L) + rank, want);
+}
+
+__global__ void __launch_bounds__(256) k_publish(Peers peers, Layout L, int rank, uint32_t step, const uint32_t *src, int n_words,
+                                                 uint32_t *local_copy)
+{
+    __shared__ int ok;
+    publish_block(peers, L, rank, step, src, n_words, local_copy, &ok);
+}
+
+__global__ void __launch_bounds__(256) k_collect(Peers peers, Layout L, int rank, uint32_t step, uint32_t *out)
+{
+    __shared__ int ok;
+    collect_block(peers, L, rank, step, out, &ok);
 }
 
 }  // namespace
@@ -160,17 +190,20 @@ __global__ void k_collect(Peers peers, Layout L, int rank, uint32_t step, uint32
 struct lv_exchange {
     int device = 0, rank = 0, world = 1;
     Layout L{};
-    uint32_t *local = nullptr;       // cudaMalloc'ed, IPC-exportable
+    unsigned long long *local = nullptr;   // cudaMalloc'ed, IPC-exportable
     Peers peers{};
-    bool opened[kMaxWorld] = {};     // peers.p[r] came from cudaIpcOpenMemHandle
+    bool opened[kMaxWorld] = {};           // peers.p[r] came from cudaIpcOpenMemHandle
     bool connected = false;
-    uint64_t published = 0, collected = 0;
-    // lv_exchange_step: the side stream the pushes / collects run on, ring of events and of collected tables
-    cudaStream_t side = nullptr;
-    cudaEvent_t *ev_kernel = nullptr, *ev_collected = nullptr;   // depth each
-    uint32_t *tables = nullptr;                                  // depth x world x slot_words
-    uint64_t steps = 0;                                          // next step of lv_exchange_step
-    int lag = 2;                                                 // step k's table is collected when step k+lag is issued
+    uint64_t published = 0, collected = 0; // steps whose publish / collect has been enqueued
+    // lv_exchange_step
+    cudaStream_t side = nullptr;           // the pushes / collects run here, never in the caller's stream
+    cudaEvent_t *ev_kernel = nullptr;      // [depth] fused kernel of the step in this ring slot has finished
+    cudaEvent_t *ev_pushed = nullptr;      // [depth] the push of the step in this ring slot has read its row
+    uint32_t *tables = nullptr;            // ring of collected tables: depth x world x slot_words
+    uint32_t *own = nullptr;               // ring of this rank's own blocks (what the fused kernels accumulate into)
+    uint64_t steps = 0;                    // next step of lv_exchange_step
+    bool stepping = false;
+    int lag = 0;                           // step k's table is collected when step k+lag is issued (or on result)
 };
 
 namespace {
@@ -196,7 +229,7 @@ size_t lv_exchange_bytes(int world, int depth, int slot_words)
 {
     if (world < 1 || world > kMaxWorld || depth < 2 || slot_words < 1) return 0;
     Layout L{world, depth, slot_words};
-    return L.words() * sizeof(uint32_t);
+    return L.bytes();
 }
 
 int lv_exchange_create(int device, int rank, int world, int depth, int slot_words, lv_exchange **out)
@@ -215,9 +248,11 @@ int lv_exchange_create(int device, int rank, int world, int depth, int slot_word
     if (!x) return LV_E_NOMEM;
     x->device = device; x->rank = rank; x->world = world;
     x->L = Layout{world, depth, slot_words};
-    const size_t bytes = x->L.words() * sizeof(uint32_t);
+    // a step's table is collected lag + 1 steps later: peers may run up to ~depth/2 steps apart before anyone waits
+    x->lag = depth / 2 < depth - 2 ? depth / 2 : depth - 2;
+    const size_t bytes = x->L.bytes();
     cudaError_t e = cudaMalloc(&x->local, bytes);
-    if (e == cudaSuccess) e = cudaMemset(x->local, 0, bytes);
+    if (e == cudaSuccess) e = cudaMemset(x->local, 0, bytes);       // sequence number 0 = "nothing has arrived"
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         int rc = x_fail(e, "exchange buffer");
@@ -241,12 +276,13 @@ void lv_exchange_destroy(lv_exchange *x)
     if (x->ev_kernel)
         for (int i = 0; i < x->L.depth; i++) {
             if (x->ev_kernel[i]) cudaEventDestroy(x->ev_kernel[i]);
-            if (x->ev_collected[i]) cudaEventDestroy(x->ev_collected[i]);
+            if (x->ev_pushed[i]) cudaEventDestroy(x->ev_pushed[i]);
         }
     delete[] x->ev_kernel;
-    delete[] x->ev_collected;
+    delete[] x->ev_pushed;
     if (x->side) cudaStreamDestroy(x->side);
     cudaFree(x->tables);
+    cudaFree(x->own);
     cudaFree(x->local);
     delete x;
 }
@@ -277,7 +313,7 @@ int lv_exchange_connect(lv_exchange *x, const unsigned char *handles)
         memcpy(&h, handles + 64 * (size_t)r, 64);
         void *p = nullptr;
         X_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-        x->peers.p[r] = (uint32_t *)p;
+        x->peers.p[r] = (unsigned long long *)p;
         x->opened[r] = true;
     }
     x->connected = true;
@@ -293,28 +329,19 @@ int lv_exchange_connect_ptrs(lv_exchange *x, void *const *peer_buffers)
     for (int r = 0; r < x->world; r++) {
         if (r == x->rank) continue;
         if (!peer_buffers[r]) return LV_E_ARG;
-        x->peers.p[r] = (uint32_t *)peer_buffers[r];
+        x->peers.p[r] = (unsigned long long *)peer_buffers[r];
     }
     x->connected = true;
     return LV_OK;
 }
 
-/* where the fused kernel must write this rank's block of step `step` (pass it as d_summary): row `rank` of ring slot
- * step % depth of the LOCAL buffer, slot_words u32 */
-uint32_t *lv_exchange_local_block(lv_exchange *x, uint64_t step)
+/* ---- the two halves on their own (any stream order the caller likes) -------------------------------------------- */
+int lv_exchange_publish(lv_exchange *x, uint64_t step, const uint32_t *d_block, int n_words, void *cuda_stream)
 {
-    if (!x) return nullptr;
-    const int slot = (int)(step % (uint64_t)x->L.depth);
-    return x->local + ((size_t)slot * x->world + x->rank) * x->L.slot_words;
-}
-
-int lv_exchange_publish(lv_exchange *x, uint64_t step, int n_words, uint32_t *d_local_copy, void *cuda_stream)
-{
-    if (!x || n_words < 0 || n_words > x->L.slot_words) return LV_E_ARG;
-    if (!x->connected || step != x->published) return LV_E_STATE;      // steps are published in order, once
+    if (!x || n_words < 0 || n_words > x->L.slot_words || (n_words > 0 && !d_block)) return LV_E_ARG;
+    if (!x->connected || x->stepping || step != x->published) return LV_E_STATE;      // steps are published in order, once
     DevGuard g(x->device);
-    k_publish<<<1, 32 * x->world, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, (uint32_t)step, n_words,
-                                                                      d_local_copy);
+    k_publish<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, (uint32_t)step, d_block, n_words, nullptr);
     X_CUDA(cudaGetLastError());
     x->published++;
     return LV_OK;
@@ -325,7 +352,7 @@ int lv_exchange_collect(lv_exchange *x, uint64_t step, uint32_t *d_table, void *
 {
     if (!x) return LV_E_ARG;
     // steps are collected in order, once, and only after this rank has published its own block of that step
-    if (!x->connected || step != x->collected || step >= x->published) return LV_E_STATE;
+    if (!x->connected || x->stepping || step != x->collected || step >= x->published) return LV_E_STATE;
     DevGuard g(x->device);
     k_collect<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, (uint32_t)step, d_table);
     X_CUDA(cudaGetLastError());
@@ -339,14 +366,13 @@ int lv_exchange_error(lv_exchange *x)
     if (!x) return LV_E_ARG;
     DevGuard g(x->device);
     uint32_t v = 0;
-    X_CUDA(cudaMemcpy(&v, x->local + x->L.err_off(), sizeof v, cudaMemcpyDeviceToHost));
+    X_CUDA(cudaMemcpy(&v, reinterpret_cast<uint32_t *>(x->local) + x->L.err_off32(), sizeof v, cudaMemcpyDeviceToHost));
     return (int)v;
 }
 
-// ---- the whole sharded step in one call ------------------------------------------------------------------------------
-// lv_exchange_step = lv_convert_diff_batch writing its summary straight into this rank's block of the ring, then (on the
-// exchange's own side stream, behind an event) the push to every peer and the collect of step k - lag.  The caller's
-// stream only ever waits for the collect of step k - depth, which finished long ago unless a peer is a ring behind.
+/* ---- the whole sharded step in one call -------------------------------------------------------------------------- */
+}  // extern "C"
+
 namespace {
 int ensure_step_state(lv_exchange *x)
 {
@@ -354,13 +380,14 @@ int ensure_step_state(lv_exchange *x)
     const int d = x->L.depth;
     X_CUDA(cudaStreamCreateWithFlags(&x->side, cudaStreamNonBlocking));
     x->ev_kernel = new (std::nothrow) cudaEvent_t[d]();
-    x->ev_collected = new (std::nothrow) cudaEvent_t[d]();
-    if (!x->ev_kernel || !x->ev_collected) return LV_E_NOMEM;
+    x->ev_pushed = new (std::nothrow) cudaEvent_t[d]();
+    if (!x->ev_kernel || !x->ev_pushed) return LV_E_NOMEM;
     for (int i = 0; i < d; i++) {
         X_CUDA(cudaEventCreateWithFlags(&x->ev_kernel[i], cudaEventDisableTiming));
-        X_CUDA(cudaEventCreateWithFlags(&x->ev_collected[i], cudaEventDisableTiming));
+        X_CUDA(cudaEventCreateWithFlags(&x->ev_pushed[i], cudaEventDisableTiming));
     }
     X_CUDA(cudaMalloc(&x->tables, sizeof(uint32_t) * (size_t)d * x->world * x->L.slot_words));
+    X_CUDA(cudaMalloc(&x->own, sizeof(uint32_t) * (size_t)d * x->L.slot_words));
     return LV_OK;
 }
 
@@ -368,14 +395,16 @@ int collect_through(lv_exchange *x, uint64_t step)
 {
     while (x->collected <= step) {
         const uint64_t j = x->collected;
-        const int slot = (int)(j % (uint64_t)x->L.depth);
-        int rc = lv_exchange_collect(x, j, x->tables + (size_t)slot * x->world * x->L.slot_words, x->side);
-        if (rc != LV_OK) return rc;
-        X_CUDA(cudaEventRecord(x->ev_collected[slot], x->side));
+        k_collect<<<1, 256, 0, x->side>>>(x->peers, x->L, x->rank, (uint32_t)j,
+                                          x->tables + (size_t)(j % (uint64_t)x->L.depth) * x->world * x->L.slot_words);
+        X_CUDA(cudaGetLastError());
+        x->collected = j + 1;
     }
     return LV_OK;
 }
 }  // namespace
+
+extern "C" {
 
 int lv_exchange_step(lv_exchange *x, lv_ctx *ctx, const uint8_t *d_i420, int first_stream, int n_streams, int n_frames,
                      uint8_t *d_bgr, uint16_t *d_mask_bits, uint8_t *d_mask_bytes, uint16_t *d_mb_count, uint8_t *d_mb_map,
@@ -384,20 +413,23 @@ int lv_exchange_step(lv_exchange *x, lv_ctx *ctx, const uint8_t *d_i420, int fir
     if (!x || !ctx || n_streams < 0 || n_frames < 0) return LV_E_ARG;
     const long long n_words = 2LL * n_streams * n_frames;
     if (n_words > x->L.slot_words) return LV_E_ARG;
-    if (!x->connected || x->steps != x->published) return LV_E_STATE;    // not mixed with manual publish calls
+    if (!x->connected) return LV_E_STATE;
+    if (!x->stepping && (x->published != 0 || x->collected != 0)) return LV_E_STATE;    // not mixed with the manual halves
     DevGuard g(x->device);
     int rc = ensure_step_state(x);
     if (rc != LV_OK) return rc;
+    x->stepping = true;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const uint64_t k = x->steps;
     const int slot = (int)(k % (uint64_t)x->L.depth);
+    uint32_t *block = x->own + (size_t)slot * x->L.slot_words;
     if (k >= (uint64_t)x->L.depth) {
-        // the fused kernel of step k overwrites this rank's block in ring slot `slot`: step k-depth must have left it
-        rc = collect_through(x, k - (uint64_t)x->L.depth);
-        if (rc != LV_OK) return rc;
-        X_CUDA(cudaStreamWaitEvent(st, x->ev_collected[slot], 0));
+        // The fused kernel of step k re-uses the row of step k-depth: its push must have read it.  That happened depth-1
+        // steps ago, so ask on the host and make the caller's stream wait only if it really has not.
+        const cudaError_t q = cudaEventQuery(x->ev_pushed[slot]);
+        if (q == cudaErrorNotReady) X_CUDA(cudaStreamWaitEvent(st, x->ev_pushed[slot], 0));
+        else if (q != cudaSuccess) return x_fail(q, "cudaEventQuery");
     }
-    uint32_t *block = lv_exchange_local_block(x, k);
     if (n_words > 0) {
         rc = lv_convert_diff_batch(ctx, d_i420, first_stream, n_streams, n_frames, d_bgr, d_mask_bits, d_mask_bytes, d_mb_count,
                                    d_mb_map, block, cuda_stream);
@@ -405,9 +437,11 @@ int lv_exchange_step(lv_exchange *x, lv_ctx *ctx, const uint8_t *d_i420, int fir
     }
     X_CUDA(cudaEventRecord(x->ev_kernel[slot], st));
     X_CUDA(cudaStreamWaitEvent(x->side, x->ev_kernel[slot], 0));
-    rc = lv_exchange_publish(x, k, (int)n_words, d_summary, x->side);
-    if (rc != LV_OK) return rc;
-    x->steps++;
+    k_publish<<<1, 256, 0, x->side>>>(x->peers, x->L, x->rank, (uint32_t)k, block, (int)n_words, d_summary);
+    X_CUDA(cudaGetLastError());
+    X_CUDA(cudaEventRecord(x->ev_pushed[slot], x->side));
+    x->published = k + 1;
+    x->steps = k + 1;
     if (k >= (uint64_t)x->lag) {
         rc = collect_through(x, k - (uint64_t)x->lag);
         if (rc != LV_OK) return rc;
@@ -416,12 +450,17 @@ int lv_exchange_step(lv_exchange *x, lv_ctx *ctx, const uint8_t *d_i420, int fir
     return LV_OK;
 }
 
+/* Kept for callers written against the in-stream variant: every push is already on its way when lv_exchange_step
+ * returns, so there is nothing to flush. */
+int lv_exchange_flush(lv_exchange *x) { return x ? LV_OK : LV_E_ARG; }
+
 /* Table of `step` (world rows of slot_words u32, device memory owned by the exchange, valid until `depth` further steps
- * have been issued).  Blocks the host until every rank's block of that step has arrived. */
+ * have been issued).  Blocks the host until every rank's block of that step has arrived; afterwards the caller's
+ * d_summary of every step up to `step` holds this rank's block too. */
 int lv_exchange_result(lv_exchange *x, uint64_t step, const uint32_t **d_table)
 {
     if (!x || !d_table) return LV_E_ARG;
-    if (!x->side || step >= x->steps || x->steps - step > (uint64_t)x->L.depth) return LV_E_STATE;
+    if (!x->stepping || step >= x->steps || x->steps - step > (uint64_t)x->L.depth) return LV_E_STATE;
     DevGuard g(x->device);
     int rc = collect_through(x, step);
     if (rc != LV_OK) return rc;

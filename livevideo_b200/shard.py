@@ -45,6 +45,9 @@ class PendingGather:
         self.work, self.out = work, out
         self.n_streams, self.n_frames, self.world, self.cap = n_streams, n_frames, world, cap
 
+    def flush(self):
+        """Nothing to do: the collective was started when the handle was made (same interface as PendingPeerGather)."""
+
     def result(self):
         import torch
         if self.work is not None:
@@ -162,12 +165,9 @@ class PeerExchange:
         for x in exchanges:
             x._capi.check(x._capi.lib().lv_exchange_connect_ptrs(x._h, ptrs), "lv_exchange_connect_ptrs")
 
-    def local_block_ptr(self, step: int) -> int:
-        return int(self._capi.lib().lv_exchange_local_block(self._h, step) or 0)
-
-    def publish(self, step, n_words, stream, local_copy=None):
-        cp = None if local_copy is None else local_copy.data_ptr()
-        self._capi.check(self._capi.lib().lv_exchange_publish(self._h, step, n_words, cp, stream.cuda_stream),
+    def publish(self, step, block, n_words, stream):
+        """Push `n_words` int32 words of `block` (a CUDA tensor) as this rank's block of `step` (manual half)."""
+        self._capi.check(self._capi.lib().lv_exchange_publish(self._h, step, block.data_ptr(), n_words, stream.cuda_stream),
                          "lv_exchange_publish")
 
     def collect(self, step, table, stream):
@@ -196,6 +196,10 @@ class PeerExchange:
             stream.cuda_stream, self._C.byref(k)), "lv_exchange_step")
         return k.value
 
+    def flush(self):
+        """Push the newest step's block now (it otherwise travels in front of the next step); asynchronous."""
+        self._capi.check(self._capi.lib().lv_exchange_flush(self._h), "lv_exchange_flush")
+
     def result(self, step):
         """int32 CUDA tensor [world, slot_words]: the table of `step` (a copy; blocks until every block has arrived)."""
         from .api import _DevView
@@ -212,6 +216,11 @@ class PendingPeerGather:
 
     def __init__(self, owner, step, n_frames):
         self.owner, self.step, self.n_frames = owner, step, n_frames
+
+    def flush(self):
+        """Make this rank's block of the newest step travel now (one host thread driving several ranks calls this on
+        every rank before asking any of them for the result)."""
+        self.owner.exchange.flush()
 
     def result(self):
         import torch

@@ -614,44 +614,41 @@ def _local_exchanges(world, slot_words, depth=8):
 
 
 def test_peer_exchange_ring_on_one_gpu(lv, torch_cuda):
-    """G ranks in one process on one GPU (raw pointers instead of IPC): over many more steps than the ring is deep,
-    every rank's table of every step holds every rank's block, and no wait ever gives up."""
+    """The two halves on their own, G ranks in one process on one GPU (raw pointers instead of IPC): over many more
+    steps than the ring is deep, every rank's table of every step holds every rank's block (short blocks are padded
+    with zeros), and no wait ever gives up."""
     torch = torch_cuda
     torch.cuda.set_device(0)                        # an earlier multi-GPU test may have left another device current
-    G, words, depth, steps = 3, 20, 4, 23           # 20 words: the scalar copy path; not a multiple of the ring
+    G, words, depth, steps = 3, 20, 4, 23           # not a multiple of the ring
     xs = _local_exchanges(G, words, depth)
     streams = [torch.cuda.Stream() for _ in range(G)]
     tables = [[torch.zeros(G * words, dtype=torch.int32, device="cuda") for _ in range(steps)] for _ in range(G)]
-    copies = [torch.zeros(words, dtype=torch.int32, device="cuda") for _ in range(G)]
     rng = np.random.default_rng(5)
-    blocks = rng.integers(0, 2**31 - 1, size=(steps, G, words), dtype=np.int64).astype(np.int32)
+    blocks = rng.integers(-2**31, 2**31 - 1, size=(steps, G, words), dtype=np.int64).astype(np.int32)
+    used = [words, words - 3, 1]                    # rank r publishes used[r] words; the rest of its row must read 0
+    want = blocks.copy()
+    for r in range(G):
+        want[:, r, used[r]:] = 0
     d_blocks = torch.from_numpy(blocks).cuda()
     torch.cuda.synchronize()
     lag = 2
     for k in range(steps + lag):
         for r in range(G):
-            with torch.cuda.stream(streams[r]):
-                if k < steps:
-                    # stand-in for the fused kernel: write this rank's block of step k in place
-                    dst = xs[r].local_block_ptr(k)
-                    holder = type("P", (), {"__cuda_array_interface__": {
-                        "shape": (words,), "typestr": "<i4", "data": (dst, False), "version": 2}})()
-                    torch.as_tensor(holder, device="cuda").copy_(d_blocks[k, r])
-                    xs[r].publish(k, words, streams[r], local_copy=copies[r])
-                if k >= lag:
-                    xs[r].collect(k - lag, tables[r][k - lag], streams[r])
+            if k < steps:
+                xs[r].publish(k, d_blocks[k, r], used[r], streams[r])
+            if k >= lag:
+                xs[r].collect(k - lag, tables[r][k - lag], streams[r])
     torch.cuda.synchronize()
     for r in range(G):
         assert xs[r].error() == 0
         for k in range(steps):
-            assert np.array_equal(tables[r][k].cpu().numpy().reshape(G, words), blocks[k]), (r, k)
-        assert np.array_equal(copies[r].cpu().numpy(), blocks[steps - 1, r])
+            assert np.array_equal(tables[r][k].cpu().numpy().reshape(G, words), want[k]), (r, k)
     # call-order errors are reported, not executed
     from livevideo_b200.capi import LiveVideoError
     with pytest.raises(LiveVideoError):
-        xs[0].publish(steps + 5, words, streams[0])          # not the next step
+        xs[0].publish(steps + 5, d_blocks[0, 0], words, streams[0])      # not the next step
     with pytest.raises(LiveVideoError):
-        xs[0].collect(steps, None, streams[0])               # not published yet
+        xs[0].collect(steps, None, streams[0])                           # not published yet
     for x in xs:
         x.close()
 
@@ -683,6 +680,8 @@ def test_sharded_step_async_over_peer_exchange_equals_single_rank(lv, orc, torch
             with torch.cuda.stream(streams[r]):
                 handles.append(sc.step_async(d_in, T, outs[r]))
         if k % 3 == 2 or k == steps - 1:                     # ask only now and then: the others are retired unread
+            for hd in handles:                               # one host thread drives both ranks: push both blocks first
+                hd.flush()
             for r, hd in enumerate(handles):
                 got = hd.result().cpu().numpy().view(np.uint32)
                 assert np.array_equal(got, want[k]), (k, r)
