@@ -833,3 +833,26 @@ def test_more_than_65535_frames_per_call(lv, orc, torch_cuda):
     ctx.convert_batch(d_in, n, d_bgr)
     assert np.array_equal(d_bgr.cpu().numpy(), ref["bgr"])
     ctx.close()
+
+
+def test_convert_diff_batch_ex_prezeroed_summary(lv, orc, torch_cuda):
+    """lv_convert_diff_batch_ex with LV_STEP_SUMMARY_PREZEROED skips the summary memset: same results when the caller
+    zeroed the buffer, and (what the flag means) the blocks ADD into whatever the buffer held."""
+    torch = torch_cuda
+    w, h, ns, nf = 352, 288, 2, 3
+    frames = orc.gen_batch("camera", 13, ns, nf, w, h)
+    ref = orc.convert_diff_batch(frames, np.zeros((ns, w * h), np.uint8), ns, nf, w, h, 20, 0, want_mask=False)
+    d_in = torch.from_numpy(frames.reshape(-1)).cuda()
+    L = lv.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    for base in (0, 7):
+        ctx = lv.Context(w, h, ns)
+        out = ctx.alloc_outputs(ns * nf)
+        out["summary"].fill_(base)
+        rc = L.lv_convert_diff_batch_ex(ctx._h, d_in.data_ptr(), 0, ns, nf, out["bgr"].data_ptr(), None, None,
+                                        out["mb_count"].data_ptr(), out["mb_map"].data_ptr(), out["summary"].data_ptr(), st, 1)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(out["bgr"].cpu().numpy(), ref["bgr"])
+        assert np.array_equal(out["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2), ref["summary"] + base)
+        ctx.close()
