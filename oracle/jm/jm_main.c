@@ -11,6 +11,11 @@
  *         runs the reference's OWN img2buf (lib/JM/output.c:87-178) with symbol_size_in_bytes = 1 on one imgpel plane
  *         read from stdin: the known-answer source that pins the oracle's restatement of the narrowing + cropping
  *
+ *     jm_ldecod  --nearlyzero  > table.u8
+ *         evaluates the reference's OWN macro IsNearlyZero (lib/JM/image.h:22, as compiled here) for every difference
+ *         a in [-255, 255] and every tol in [0, 255]: 511 x 256 bytes of 0/1, row = a + 255.  Pins the oracle's
+ *         lvo_is_nearly_zero, i.e. the per-pixel rule "changed <=> !IsNearlyZero(cur - ref, tol)".
+ *
  * Frames leave the decoder through write_out_picture (lib/JM/output.c:362-453): Y, U, V, 8 bit, cropped.
  * "-" writes them to stdout (a pipe to the GPU harness).  width/height size the author's analysis
  * buffers that his hooks in the macroblock decoder write unconditionally (curr_frm, curr_res:
@@ -78,10 +83,26 @@ static int img2buf_mode(char **a)
     return 0;
 }
 
+static int nearlyzero_mode(void)
+{
+    static unsigned char t[511 * 256];
+    int a, tol;
+    size_t put = 0;
+    for (a = -255; a <= 255; a++)
+        for (tol = 0; tol <= 255; tol++) t[(a + 255) * 256 + tol] = IsNearlyZero(a, tol) ? 1 : 0;   /* image.h:22 */
+    while (put < sizeof t) {
+        ssize_t r = write(1, t + put, sizeof t - put);
+        if (r <= 0) return 5;
+        put += (size_t)r;
+    }
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     int w, h, mbs;
     if (argc == 8 && strcmp(argv[1], "--img2buf") == 0) return img2buf_mode(argv + 2);
+    if (argc == 2 && strcmp(argv[1], "--nearlyzero") == 0) return nearlyzero_mode();
     if (argc < 5) {
         fprintf(stderr, "usage: %s stream.264 out.yuv|- width height\n", argv[0]);
         return 2;

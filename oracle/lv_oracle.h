@@ -15,9 +15,11 @@
  *
  * Parity status: the conversion is PINNED -- tests check it against the reference's original
  * object code (oracle/_ref/oracle32, built by oracle/ref32/build_ref.py) on all 2^24 (Y,U,V)
- * triples and against the golden digests of SURVEY.md section 8(c).  The difference/macroblock
- * part has no upstream test or binary: "parity unpinned" by the reference, pinned by the cited
- * source lines only.
+ * triples and against the golden digests of SURVEY.md section 8(c).  The difference primitive
+ * (lvo_is_nearly_zero) and img2buf are PINNED against the reference's own C as compiled into
+ * oracle/_ref/jm_ldecod (--nearlyzero: all 511 x 256 pairs; --img2buf), tests/golden/*.json.  The
+ * loops around the primitive and the macroblock scan have no upstream test or callable binary:
+ * "parity unpinned" by the reference, pinned by the cited source lines only.
  */
 #ifndef LV_ORACLE_H
 #define LV_ORACLE_H

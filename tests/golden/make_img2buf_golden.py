@@ -46,6 +46,22 @@ def main():
     with open(os.path.join(HERE, "img2buf.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(f"wrote {len(out['cases'])} cases")
+    # the difference primitive: the reference's own macro IsNearlyZero (lib/JM/image.h:22) as compiled into jm_ldecod,
+    # for every a in [-255, 255] (rows) and tol in [0, 255] (columns)
+    import subprocess
+    exe = os.path.join(HERE, "..", "..", "oracle", "_ref", "jm_ldecod")
+    tab = np.frombuffer(subprocess.run([exe, "--nearlyzero"], capture_output=True, check=True).stdout, dtype=np.uint8)
+    assert tab.size == 511 * 256
+    t = tab.reshape(511, 256)
+    nz = {"generator": "oracle/_ref/jm_ldecod --nearlyzero = the macro IsNearlyZero of /root/reference/lib/JM/image.h:22 as compiled",
+          "rows": "a = -255..255", "cols": "tol = 0..255", "sha256": hashlib.sha256(tab.tobytes()).hexdigest(),
+          "ones": int(tab.sum()),
+          "samples": [{"a": a, "tol": tol, "nearly_zero": int(t[a + 255, tol])}
+                      for (a, tol) in [(0, 0), (1, 0), (-1, 0), (20, 20), (21, 20), (-20, 20), (-21, 20), (25, 25), (-26, 25),
+                                       (255, 255), (-255, 255), (255, 254), (-255, 254), (128, 127), (-128, 128)]]}
+    with open(os.path.join(HERE, "nearlyzero.json"), "w") as f:
+        json.dump(nz, f, indent=1)
+    print("wrote nearlyzero.json", nz["sha256"][:16], nz["ones"])
 
 
 if __name__ == "__main__":

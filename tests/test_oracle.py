@@ -310,3 +310,20 @@ def test_picture16_to_i420_plane_order_and_half_crop(orc):
     u = orc.img2buf(pic[sx * sy:sx * sy * 5 // 4], sx // 2, sy // 2, cl // 2, cr // 2, ct // 2, cb // 2)
     v = orc.img2buf(pic[sx * sy * 5 // 4:], sx // 2, sy // 2, cl // 2, cr // 2, ct // 2, cb // 2)
     assert out.size == w * h * 3 // 2 and np.array_equal(out, np.concatenate([y, u, v]))
+
+
+def test_is_nearly_zero_matches_the_reference_macro_as_compiled(orc):
+    """tests/golden/nearlyzero.json holds the reference's own macro IsNearlyZero (lib/JM/image.h:22), compiled into
+    oracle/_ref/jm_ldecod, evaluated on every difference a in [-255, 255] and every tol in [0, 255]: the oracle's
+    restatement -- and with it the rule 'changed <=> |cur - ref| > tol' -- agrees on all 130 816 pairs."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "nearlyzero.json")) as f:
+        g = json.load(f)
+    tab = np.array([[orc.lib().lvo_is_nearly_zero(a, tol) for tol in range(256)] for a in range(-255, 256)], dtype=np.uint8)
+    assert int(tab.sum()) == g["ones"]
+    assert hashlib.sha256(tab.tobytes()).hexdigest() == g["sha256"]
+    for s in g["samples"]:
+        assert int(tab[s["a"] + 255, s["tol"]]) == s["nearly_zero"], s
+    a = np.arange(-255, 256)[:, None]
+    assert np.array_equal(tab, (np.abs(a) <= np.arange(256)[None, :]).astype(np.uint8))     # <=> |a| <= tol
