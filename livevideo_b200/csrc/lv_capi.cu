@@ -558,15 +558,20 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
                 LV_CUDA(cudaStreamWaitEvent(c->s_copy_in, c->ev_k[slot], 0));
                 LV_CUDA(cudaStreamWaitEvent(c->s_compute, c->ev_out[slot], 0));
             }
-            // H2D: per stream one strided piece (frames t0..t0+nt of stream s are contiguous in the host batch)
-            for (int s = 0; s < ns; s++) {
-                const size_t hf = (size_t)(s0 + s) * n_frames + t0, df = (size_t)s * nt;
+            // H2D: frames t0..t0+nt of stream s are contiguous in the host batch and the streams are n_frames frames
+            // apart: ONE strided copy for the whole chunk (32 streams x 1 frame is one call, not 32)
+            {
+                const size_t hf = (size_t)s0 * n_frames + t0;
+                cudaError_t up;
                 if (pic)
-                    LV_CUDA(cudaMemcpyAsync(c->d_pic[slot] + df * pic->samples, pic->h_pic16 + hf * pic->samples,
-                                            (size_t)nt * pic->samples * sizeof(uint16_t), cudaMemcpyHostToDevice, c->s_copy_in));
+                    up = cudaMemcpy2DAsync(c->d_pic[slot], (size_t)nt * pic->samples * sizeof(uint16_t),
+                                           pic->h_pic16 + hf * pic->samples, (size_t)n_frames * pic->samples * sizeof(uint16_t),
+                                           (size_t)nt * pic->samples * sizeof(uint16_t), (size_t)ns, cudaMemcpyHostToDevice,
+                                           c->s_copy_in);
                 else
-                    LV_CUDA(cudaMemcpyAsync(c->d_in[slot] + df * g.frame, h_i420 + hf * g.frame, (size_t)nt * g.frame,
-                                            cudaMemcpyHostToDevice, c->s_copy_in));
+                    up = cudaMemcpy2DAsync(c->d_in[slot], (size_t)nt * g.frame, h_i420 + hf * g.frame, (size_t)n_frames * g.frame,
+                                           (size_t)nt * g.frame, (size_t)ns, cudaMemcpyHostToDevice, c->s_copy_in);
+                LV_CUDA(up);
             }
             LV_CUDA(cudaEventRecord(c->ev_in[slot], c->s_copy_in));
             LV_CUDA(cudaStreamWaitEvent(c->s_compute, c->ev_in[slot], 0));
@@ -582,23 +587,19 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
             if (rc != LV_OK) return rc;
             LV_CUDA(cudaEventRecord(c->ev_k[slot], c->s_compute));
             LV_CUDA(cudaStreamWaitEvent(c->s_copy_out, c->ev_k[slot], 0));
-            for (int s = 0; s < ns; s++) {
-                const size_t hf = (size_t)(s0 + s) * n_frames + t0, df = (size_t)s * nt;
-                if (h_bgr)
-                    LV_CUDA(cudaMemcpyAsync(h_bgr + hf * 3 * g.px, c->d_bgr[slot] + df * 3 * g.px, (size_t)nt * 3 * g.px,
-                                            cudaMemcpyDeviceToHost, c->s_copy_out));
-                if (h_mask_bits)
-                    LV_CUDA(cudaMemcpyAsync(h_mask_bits + hf * units, c->d_bits[slot] + df * units,
-                                            sizeof(uint16_t) * nt * units, cudaMemcpyDeviceToHost, c->s_copy_out));
-                if (h_mb_count)
-                    LV_CUDA(cudaMemcpyAsync(h_mb_count + hf * mbs, c->d_cnt[slot] + df * mbs, sizeof(uint16_t) * nt * mbs,
-                                            cudaMemcpyDeviceToHost, c->s_copy_out));
-                if (h_mb_map)
-                    LV_CUDA(cudaMemcpyAsync(h_mb_map + hf * mbs, c->d_map[slot] + df * mbs, (size_t)nt * mbs,
-                                            cudaMemcpyDeviceToHost, c->s_copy_out));
-                if (h_summary)
-                    LV_CUDA(cudaMemcpyAsync(h_summary + hf * 2, c->d_sum[slot] + df * 2, sizeof(uint32_t) * 2 * nt,
-                                            cudaMemcpyDeviceToHost, c->s_copy_out));
+            {
+                // D2H: the same strided shape per output (width = this chunk's nt frames of one stream, height = streams)
+                const size_t hf = (size_t)s0 * n_frames + t0;
+                auto down = [&](void *h_base, const void *d_base, size_t bytes_per_frame) -> cudaError_t {
+                    return cudaMemcpy2DAsync(static_cast<uint8_t *>(h_base) + hf * bytes_per_frame, (size_t)n_frames * bytes_per_frame,
+                                             d_base, (size_t)nt * bytes_per_frame, (size_t)nt * bytes_per_frame, (size_t)ns,
+                                             cudaMemcpyDeviceToHost, c->s_copy_out);
+                };
+                if (h_bgr) LV_CUDA(down(h_bgr, c->d_bgr[slot], 3 * g.px));
+                if (h_mask_bits) LV_CUDA(down(h_mask_bits, c->d_bits[slot], sizeof(uint16_t) * units));
+                if (h_mb_count) LV_CUDA(down(h_mb_count, c->d_cnt[slot], sizeof(uint16_t) * mbs));
+                if (h_mb_map) LV_CUDA(down(h_mb_map, c->d_map[slot], mbs));
+                if (h_summary) LV_CUDA(down(h_summary, c->d_sum[slot], sizeof(uint32_t) * 2));
             }
             LV_CUDA(cudaEventRecord(c->ev_out[slot], c->s_copy_out));
         }
