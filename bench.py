@@ -358,6 +358,44 @@ def run_ours(args):
                "pcie_gbs": (h2d + d2h) * e_steps / dt / 1e9}
         if e_ns != ns:
             e2e["sample"] = f"{e_ns} of this rank's {ns} streams per host step (pinned-memory bound)"
+        # The literal drop-in entries, one synchronous call per picture with host pointers (what the reference's dialogs
+        # do, MainDlg.cpp:946-974): YV12_to_RGB24 + FrameDiff_MB on the application's own buffers, pinned in place
+        # with lv_host_register.  Reported beside the batched host step; rank 0 only.
+        if rank == 0:
+            try:
+                import mmap
+                px1 = w * h
+
+                def own(nb):
+                    return np.frombuffer(mmap.mmap(-1, nb), dtype=np.uint8, count=nb)
+                by, bu, bv, bref, bdst, bmask = own(px1), own(px1 // 4), own(px1 // 4), own(px1), own(3 * px1), own(px1)
+                fr0 = h_in.array[: ctx.frame_bytes]
+                by[:], bu[:], bv[:] = fr0[:px1], fr0[px1:px1 + px1 // 4], fr0[px1 + px1 // 4:]
+                bref[:] = 0
+                for a in (by, bu, bv, bref, bdst, bmask):
+                    lv.host_register(a)
+                csc = lv.ColorSpaceConversions()
+                cnt1 = np.zeros(ctx.mbs, np.uint16)
+                map1 = np.zeros(ctx.mbs, np.uint8)
+                for _ in range(3):
+                    csc.YV12_to_RGB24(by, bu, bv, bdst, w, h)
+                    lv.FrameDiff_MB(by, bref, w, h, 20, 0, mask=bmask, mb_count=cnt1, mb_map=map1)
+                calls = 32
+                t0 = time.perf_counter()
+                for _ in range(calls):
+                    csc.YV12_to_RGB24(by, bu, bv, bdst, w, h)
+                t1 = time.perf_counter()
+                for _ in range(calls):
+                    lv.FrameDiff_MB(by, bref, w, h, 20, 0, mask=bmask, mb_count=cnt1, mb_map=map1)
+                t2 = time.perf_counter()
+                e2e["drop_in_calls"] = {
+                    "what": "one synchronous call per picture, host pointers pinned in place (lv_host_register)",
+                    "YV12_to_RGB24_us": (t1 - t0) / calls * 1e6, "FrameDiff_MB_us": (t2 - t1) / calls * 1e6,
+                    "both_mpx_s": px1 * calls / (t2 - t0) / 1e6}
+                for a in (by, bu, bv, bref, bdst, bmask):
+                    lv.host_unregister(a)
+            except Exception as ex:  # noqa: BLE001
+                e2e["drop_in_calls"] = {"error": repr(ex)}
         # sanity: the host path returned the same summaries as the device path
         a = h_sum.array.view(np.uint32).reshape(e_ns, nf, 2)[:, 1:]
         b = out["summary"].cpu().numpy().view(np.uint32).reshape(ns, nf, 2)[:e_ns, 1:]
