@@ -95,6 +95,13 @@ LV_API int lv_create(int device, int width, int height, int max_streams, int tol
                      lv_ctx **out);
 LV_API void lv_destroy(lv_ctx *ctx);
 LV_API int lv_set_params(lv_ctx *ctx, int tol, int mb_thresh);
+/* What a frame is differenced against in the fused step.  LV_REF_PREVIOUS (default): frame t-1, the first frame of a
+ * batch against the carried previous luma (prev_frm, lib/JM/image.c:1553-1561).  LV_REF_STATIC: every frame of a stream
+ * against the stream's stored plane -- the static background BkdBuf of MainDlg.cpp:238-246, set with lv_set_prev_luma --
+ * which the step then leaves untouched. */
+#define LV_REF_PREVIOUS 0
+#define LV_REF_STATIC   1
+LV_API int lv_set_ref_mode(lv_ctx *ctx, int mode);
 
 /* Geometry helpers (bytes / element counts per frame). */
 LV_API size_t lv_frame_bytes_i420(const lv_ctx *ctx);   /* 1.5*w*h            */

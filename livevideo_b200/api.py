@@ -170,6 +170,11 @@ class Context:
             capi.check(capi.lib().lv_set_prev_luma(self._h, stream, _dev_ptr(y, torch.uint8, self.px, "y", self.device),
                                                    1, _stream_handle(cuda_stream)), "lv_set_prev_luma")
 
+    def set_ref_mode(self, static: bool):
+        """static=True: every frame is differenced against the stream's stored plane (the static background of
+        MainDlg.cpp:238-246, set with set_prev_luma), which is left untouched; False: against the previous frame."""
+        capi.check(capi.lib().lv_set_ref_mode(self._h, 1 if static else 0), "lv_set_ref_mode")
+
     def get_prev_luma(self, stream, cuda_stream=None):
         out = np.empty(self.px, dtype=np.uint8)
         capi.check(capi.lib().lv_get_prev_luma(self._h, stream, out.ctypes.data, 0, _stream_handle(cuda_stream)),

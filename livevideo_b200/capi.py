@@ -26,6 +26,7 @@ SYMBOLS = {
     "lv_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "lv_destroy": (None, [_vp]),
     "lv_set_params": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "lv_set_ref_mode": (C.c_int, [_vp, C.c_int]),
     "lv_frame_bytes_i420": (C.c_size_t, [_vp]),
     "lv_frame_bytes_bgr": (C.c_size_t, [_vp]),
     "lv_frame_mask_units": (C.c_size_t, [_vp]),

@@ -49,6 +49,7 @@ struct lv_ctx {
     int tol = 20, mb_thresh = 0;
     uint8_t *state[2] = {nullptr, nullptr};   // ping-pong previous-luma planes, max_streams x px each
     int cur = 0;                              // state[cur] holds the live previous luma
+    int ref_mode = 0;                         // LV_REF_PREVIOUS / LV_REF_STATIC
     uint64_t launches = 0;
     // host-step pipeline (created on first lv_step_host)
     cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
@@ -217,6 +218,13 @@ void lv_destroy(lv_ctx *c)
     delete c;
 }
 
+int lv_set_ref_mode(lv_ctx *c, int mode)
+{
+    if (!c || (mode != LV_REF_PREVIOUS && mode != LV_REF_STATIC)) return LV_E_ARG;
+    c->ref_mode = mode;
+    return LV_OK;
+}
+
 int lv_set_params(lv_ctx *c, int tol, int mb_thresh)
 {
     if (!c || tol < 0 || tol > 255 || mb_thresh < 0 || mb_thresh > 256) return LV_E_ARG;
@@ -291,6 +299,12 @@ int lv_convert_diff_batch_ex(lv_ctx *c, const uint8_t *d_i420, int first_stream,
     a.tol = c->tol; a.mb_thresh = c->mb_thresh;
     a.bgr = d_bgr; a.mask_bits = d_mask_bits; a.mask_bytes = d_mask_bytes;
     a.mb_count = d_mb_count; a.mb_map = d_mb_map; a.summary = d_summary;
+    if (c->ref_mode == LV_REF_STATIC) {
+        // static background (MainDlg.cpp:238-246): the stored plane is the reference of every frame and stays as it is
+        a.static_ref = 1;
+        a.state_out = nullptr;
+        return launch_result(lv::launch_step(a, st), c->launches);
+    }
     int rc = launch_result(lv::launch_step(a, st), c->launches);
     if (rc != LV_OK) return rc;
     // Streams outside [first_stream, first_stream+n_streams) keep their state: carry it over to the

@@ -42,6 +42,7 @@ struct KArgs {
     uint32_t nf_magic;          // ceil(2^32 / n_frames): f / n_frames == umulhi(f, magic) for f < 2^16
     uint32_t mbw_magic;         // flat macroblock mapping: ceil(2^32 / mb_w), or 0 = one block row per macroblock row
     int f_base;                 // first frame index of this launch (gridDim.z is limited to 65535)
+    int static_ref;             // 1: the stream's stored plane is the reference of EVERY frame (static background)
     int tol, mb_thresh;
     uint8_t *bgr;
     uint16_t *mask_bits;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
             const int t = f - s * a.n_frames;
             const uint8_t *ref;
             if (a.ref_planes) ref = a.ref_planes + (size_t)f * g.px;
-            else ref = (t == 0) ? a.state_in + (size_t)s * g.px : yf - a.y_stride;
+            else ref = (t == 0 || a.static_ref) ? a.state_in + (size_t)s * g.px : yf - a.y_stride;
             const uint4 p0 = ld16_stream(ref + off);
             const uint4 p1 = ld16_stream(ref + off + w);
             const uint32_t tol4 = (uint32_t)a.tol * 0x01010101u;
@@ -351,11 +352,12 @@ static bool use_strip() { return kernel_variant() == 2; }
 
 int launch_step(const StepArgs &s, cudaStream_t st)
 {
-    if (use_strip())
+    if (use_strip() && !s.static_ref)
         if (int r = launch_step_strip(s, st)) return r;
-    if (use_tma())
+    if (use_tma() && !s.static_ref)
         if (int r = launch_step_tma(s, st)) return r;   // 0 = geometry/alignment not eligible for the TMA pipeline
     KArgs a{};
+    a.static_ref = s.static_ref;
     a.g = s.g; a.y0 = s.i420; a.y_stride = s.g.frame; a.ref_planes = nullptr;
     a.state_in = s.state_in; a.state_out = s.state_out; a.n_frames = s.n_frames;
     a.tol = s.tol; a.mb_thresh = s.mb_thresh;

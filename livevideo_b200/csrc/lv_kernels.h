@@ -30,6 +30,7 @@ struct StepArgs {
     const uint8_t *state_in;  // previous luma planes, n_streams x px (slot of stream s = s)
     uint8_t *state_out;       // luma of the last frame of each stream is written here (may be NULL)
     int n_streams, n_frames;
+    int static_ref;           // 1: every frame of a stream is differenced against state_in (never against frame t-1)
     int tol, mb_thresh;
     uint8_t *bgr;             // any output may be NULL
     uint16_t *mask_bits;

@@ -856,3 +856,42 @@ def test_convert_diff_batch_ex_prezeroed_summary(lv, orc, torch_cuda):
         assert np.array_equal(out["bgr"].cpu().numpy(), ref["bgr"])
         assert np.array_equal(out["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2), ref["summary"] + base)
         ctx.close()
+
+
+def test_static_background_reference_mode(lv, orc, torch_cuda):
+    """LV_REF_STATIC: every frame of a stream is differenced against the stream's stored plane (the static background
+    BkdBuf of MainDlg.cpp:238-246), which the step leaves untouched -- frame by frame the reference's primitive
+    (frame_diff_mb) against that plane; conversion unchanged; switching back resumes the previous-frame rule."""
+    torch = torch_cuda
+    w, h, ns, nf = 352, 288, 2, 4
+    frames = orc.gen_batch("camera", 17, ns, nf, w, h)
+    px = w * h
+    bg = [orc.gen("camera", 17, s, 9, w, h)[:px].copy() for s in range(ns)]
+    ctx = lv.Context(w, h, ns)
+    for s in range(ns):
+        ctx.set_prev_luma(s, bg[s])
+    ctx.set_ref_mode(True)
+    d_in = torch.from_numpy(frames.reshape(-1)).cuda()
+    out = ctx.alloc_outputs(ns * nf, mask_bytes=True)
+    for _ in range(2):                                         # twice: the background must survive the step
+        ctx.convert_diff_batch(d_in, ns, nf, out)
+        torch.cuda.synchronize()
+        got_mask = out["mask_bytes"].cpu().numpy().reshape(ns, nf, px)
+        got_cnt = out["mb_count"].cpu().numpy().view(np.uint16).reshape(ns, nf, -1)
+        got_sum = out["summary"].cpu().numpy().view(np.uint32).reshape(ns, nf, 2)
+        got_bgr = out["bgr"].cpu().numpy().reshape(ns, nf, -1)
+        for s in range(ns):
+            for t in range(nf):
+                mask, cnt, mp, changed = orc.frame_diff_mb(frames[s, t, :px], bg[s], w, h, 20, 0)
+                assert np.array_equal(got_mask[s, t], mask) and np.array_equal(got_cnt[s, t], cnt), (s, t)
+                assert got_sum[s, t, 0] == changed and got_sum[s, t, 1] == int(mp.sum())
+                assert np.array_equal(got_bgr[s, t], orc.convert_frame(frames[s, t], w, h))
+            assert np.array_equal(ctx.get_prev_luma(s), bg[s])
+    ctx.set_ref_mode(False)
+    prev = np.stack(bg)
+    ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, 20, 0)
+    ctx.convert_diff_batch(d_in, ns, nf, out)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["mask_bytes"].cpu().numpy(), ref["mask"])
+    assert np.array_equal(ctx.get_prev_luma(0), prev[0])
+    ctx.close()
