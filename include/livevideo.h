@@ -68,6 +68,22 @@ LV_API void FrameDiff_MB(const unsigned char *cur_y, const unsigned char *ref_y,
                          int tol, int mb_thresh, unsigned char *mask, unsigned short *mb_count,
                          unsigned char *mb_map);
 
+/* Several pictures per call -- the reference's real call pattern: CMainDlg::DisplayPic converts FIVE pictures back to
+ * back (MainDlg.cpp:937-977: pCon.YV12_to_RGB24(srcY[i], srcU[i], srcV[i], RGBbuf[i], width, height), i = 0..4), so the
+ * arrays the dialog already holds (unsigned char *srcY[5], ... RGBbuf[5], MainDlg.h) are passed as they are.  The upload
+ * of picture i+1, the kernel of picture i and the download of picture i-1 overlap on three streams; the call returns
+ * when every dst_ori[i] is complete.  Results are identical to n calls of YV12_to_RGB24 / FrameDiff_MB.  Host
+ * pointers (pageable, or pinned in place with lv_host_register for DMA at link speed); returns LV_OK or an LV_E_* code
+ * (never aborts).  lv_diff_host_multi: mask / mb_count / mb_map (arrays or single entries) may be NULL; when
+ * ref_y[i] == cur_y[i-1] (a sequence differenced against its own previous picture, lib/JM/image.c:1553-1561) every
+ * plane is uploaded once. */
+LV_API int lv_convert_host_multi(const unsigned char *const *src0, const unsigned char *const *src1,
+                                 const unsigned char *const *src2, unsigned char *const *dst_ori, int n, int width,
+                                 int height);
+LV_API int lv_diff_host_multi(const unsigned char *const *cur_y, const unsigned char *const *ref_y, int n, int width,
+                              int height, int tol, int mb_thresh, unsigned char *const *mask,
+                              unsigned short *const *mb_count, unsigned char *const *mb_map);
+
 /* The other five methods of ColorSpaceConversions (Convert.h:25-30; code at Convert.obj .text+0x1d0, +0x740, +0x8b0,
  * +0x960, +0xa40).  The application never calls them; they complete the Convert.h surface with the object code's
  * exact semantics (same host-pointer, synchronous, void convention as YV12_to_RGB24; w % 4 == 0, h % 4 == 0):
@@ -125,7 +141,15 @@ LV_API int lv_reset_prev_luma(lv_ctx *ctx, void *cuda_stream);   /* back to all 
  *   d_mask_bytes w*h bytes per frame, 0/1
  *   d_mb_count   mb_w*mb_h uint16 per frame;  d_mb_map  mb_w*mb_h bytes per frame
  *   d_summary    2 uint32 per frame: {changed pixels, changed macroblocks}
- * Requires width % 16 == 0 and height % 2 == 0. */
+ * Requires width % 16 == 0 and height % 2 == 0.
+ * Alignment (checked, LV_E_ARG otherwise -- the kernels move 16-byte words, and a misaligned vector access would be a
+ * sticky CUDA error): d_i420, d_bgr, d_mask_bytes 16 bytes; d_mask_bits, d_mb_count 2 bytes; d_summary 4 bytes.  The same
+ * holds for lv_convert_batch (d_i420, d_bgr) and lv_diff_batch (d_cur_y, d_ref_y, d_mask_bytes 16 bytes).
+ * lv_write_bks, lv_narrow_pictures and lv_convert_format accept any byte alignment (they fall back to narrower
+ * accesses).  Anything from cudaMalloc / a torch allocation is 256-byte aligned; only sub-buffers at odd offsets are
+ * affected.
+ * Streams keep their state independently: stepping streams [first_stream, first_stream + n_streams) neither reads nor
+ * copies the state of any other stream. */
 LV_API int lv_convert_diff_batch(lv_ctx *ctx, const uint8_t *d_i420, int first_stream, int n_streams,
                                  int n_frames, uint8_t *d_bgr, uint16_t *d_mask_bits,
                                  uint8_t *d_mask_bytes, uint16_t *d_mb_count, uint8_t *d_mb_map,
@@ -138,6 +162,27 @@ LV_API int lv_convert_diff_batch_ex(lv_ctx *ctx, const uint8_t *d_i420, int firs
                                     int n_frames, uint8_t *d_bgr, uint16_t *d_mask_bits, uint8_t *d_mask_bytes,
                                     uint16_t *d_mb_count, uint8_t *d_mb_map, uint32_t *d_summary, void *cuda_stream,
                                     int flags);
+
+/* The fused step with the step AFTER the path folded in: the object box of motion_segment's I-frame branch
+ * (lib/JM/image.c:4783-4848).  For each frame, n_objects windows {x0, x1, y0, y1} (inclusive luma coordinates; the
+ * reference's min_x, max_x, min_y, max_y of image.c:4786-4789) and, out, n_objects boxes {min_x, max_x, min_y, max_y} =
+ * the extreme coordinates of the changed pixels (bkd_obj == 1, image.c:4798-4803) inside the window (image.c:4818-4838);
+ * a window without a changed pixel yields the reference's initial values {x1+1, x0-1, y1+1, y0-1}.  The boxes are
+ * accumulated by the fused kernel itself (warp min/max reductions, at most four atomics per block and object): no mask
+ * is written to or read back from memory.  With lv_set_ref_mode(LV_REF_STATIC) and the background in the state
+ * (lv_set_prev_luma) this is the reference's background subtraction against BkdBuf; d_bgr may be NULL (the reference's
+ * step displays nothing).  d_windows / d_boxes: 4 ints per (frame, object), frame-major, 16-byte aligned.
+ *   lv_object_windows  windows from objects {PosX, PosY, Width, Height}: ClipX(PosX -+ Width/2 -+ hor_margin), ClipY(...)
+ *                      (image.c:4786-4789, image.h:23-24; the reference's margins are 8, global.h:119-120)
+ *   lv_object_update   objects from boxes under the reference's guard (image.c:4840-4848): only when min_x < max_x and
+ *                      min_y < max_y: PosX = min_x + (max_x-min_x)/2, PosY likewise, Width = max_x-min_x, Height likewise */
+#define LV_MAX_OBJECTS 16
+LV_API int lv_convert_diff_box_batch(lv_ctx *ctx, const uint8_t *d_i420, int first_stream, int n_streams, int n_frames,
+                                     uint8_t *d_bgr, uint16_t *d_mb_count, uint8_t *d_mb_map, uint32_t *d_summary,
+                                     const int *d_windows, int n_objects, int *d_boxes, void *cuda_stream);
+LV_API int lv_object_windows(lv_ctx *ctx, const int *d_objects, int n, int hor_margin, int ver_margin, int *d_windows,
+                             void *cuda_stream);
+LV_API int lv_object_update(lv_ctx *ctx, const int *d_boxes, int n, int *d_objects, void *cuda_stream);
 
 /* Conversion only (K2) and difference only (K3) over n frames; same layouts as above.
  * lv_diff_batch: frame i of d_cur_y (w*h bytes each) against frame i of d_ref_y. */
@@ -279,7 +324,16 @@ LV_API int lv_device_sm_count(const lv_ctx *ctx);
  *   lv_exchange_publish / lv_exchange_collect   the two halves on their own (not to be mixed with lv_exchange_step):
  *                          publish(step, d_block, n_words) in order, once per step; collect(step, d_table) in order,
  *                          within `depth` steps; d_table = world x slot_words u32 or NULL to retire the step unread
- *   lv_exchange_error      0, or which wait gave up after 4 s (1 publish / 2 collect): a wait never spins forever
+ *   lv_exchange_error      0, or which wait gave up (1 publish / 2 collect / 3 gate): a kernel of the exchange never
+ *                          spins for more than 4 s in all (one deadline per kernel), and once the error is set every
+ *                          later kernel returns at once; read from a host-mapped word, no copy, no synchronisation
+ *   lv_exchange_gate       device-side rendezvous of all ranks in the caller's stream (collective: same number of calls
+ *                          on every rank): what is enqueued behind it starts within microseconds of the same instant on
+ *                          every GPU, however far apart the host threads are
+ *   lv_exchange_wait_summary  makes a stream wait until the caller's d_summary of `step` has been written: with
+ *                          lv_exchange_step that buffer is filled by the push kernel on the exchange's own stream (NOT
+ *                          in-stream behind the fused kernel as in lv_convert_diff_batch); a consumer on the compute
+ *                          stream must call this first, or use the table of lv_exchange_result
  *   lv_exchange_destroy    only after every rank has collected the last step it will publish (a barrier of the
  *                          launcher): peers store into this rank's buffer until then */
 typedef struct lv_exchange lv_exchange;
@@ -299,6 +353,8 @@ LV_API int lv_exchange_result(lv_exchange *x, uint64_t step, const uint32_t **d_
 LV_API int lv_exchange_publish(lv_exchange *x, uint64_t step, const uint32_t *d_block, int n_words, void *cuda_stream);
 LV_API int lv_exchange_collect(lv_exchange *x, uint64_t step, uint32_t *d_table, void *cuda_stream);
 LV_API int lv_exchange_error(lv_exchange *x);
+LV_API int lv_exchange_gate(lv_exchange *x, void *cuda_stream);
+LV_API int lv_exchange_wait_summary(lv_exchange *x, uint64_t step, void *cuda_stream);
 LV_API const char *lv_exchange_last_error(void);
 
 #ifdef __cplusplus

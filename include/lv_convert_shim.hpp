@@ -25,6 +25,15 @@ public:
         ::YV12_to_RGB24(src0, src1, src2, dst_ori, width, height);
     }
 
+    // DisplayPic's five conversions (MainDlg.cpp:946-974) in ONE call: pCon.YV12_to_RGB24(srcY, srcU, srcV, RGBbuf, 5,
+    // width, height) with the dialog's own pointer arrays; uploads, kernels and downloads of the pictures overlap.
+    // Returns LV_OK or an LV_E_* code.
+    int YV12_to_RGB24(unsigned char *const *src0, unsigned char *const *src1, unsigned char *const *src2,
+                      unsigned char *const *dst_ori, int n, int width, int height)
+    {
+        return ::lv_convert_host_multi(src0, src1, src2, dst_ori, n, width, height);
+    }
+
     // the five converters the application never calls; same object-code semantics, same signatures
     void RGB24_to_YV12(unsigned char *in, unsigned char *out, int w, int h) { ::RGB24_to_YV12(in, out, w, h); }
     void YVU9_to_YV12(unsigned char *in, unsigned char *out, int w, int h) { ::YVU9_to_YV12(in, out, w, h); }

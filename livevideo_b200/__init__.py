@@ -4,7 +4,7 @@ Only the hot path lives here: `csrc/` (hand-written sm_100a kernels + the C ABI 
 and `api.py`, the host-side mirror of the reference interface.  Importing the package does not load
 CUDA; the first call does, and fails loudly when liblivevideo.so or a device is missing.
 """
-from .api import (DEFAULT_MB_THRESH, DEFAULT_TOL, ColorSpaceConversions, Context, FrameDiff_MB,  # noqa: F401
+from .api import (DEFAULT_MB_THRESH, DEFAULT_TOL, ColorSpaceConversions, Context, FrameDiff_MB, FrameDiff_MB_multi,  # noqa: F401
                   gen_synthetic, get_kernel_variant, host_register, host_unregister, pinned, set_kernel_variant)
 from .capi import LiveVideoError, lib, lib_path  # noqa: F401
 

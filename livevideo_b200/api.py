@@ -2,8 +2,9 @@
 
 * ``ColorSpaceConversions`` -- same class/method name and argument meaning as the reference's
   ``class ColorSpaceConversions`` (Convert.h:19-31): ``YV12_to_RGB24(src0, src1, src2, dst_ori, width, height)``
-  fills ``dst_ori`` in place (bottom-up B,G,R).  The five converters the application never calls are
-  declared and raise NotImplementedError.
+  fills ``dst_ori`` in place (bottom-up B,G,R); ``YV12_to_RGB24_multi`` converts several pictures per call the way
+  CMainDlg::DisplayPic issues them (MainDlg.cpp:937-977).  The five converters the application never calls
+  (Convert.h:25-30) are implemented too, bit-exact with the object code.
 * ``FrameDiff_MB`` -- the difference primitive extracted from lib/JM/image.c:4791-4804 / 5143-5150.
 * ``Context`` -- the batched device API (lv_create ... lv_destroy): fused conversion + difference over
   many streams with the per-stream previous-luma state of lib/JM/image.c:1553-1561.
@@ -48,6 +49,18 @@ class ColorSpaceConversions:
         capi.lib().YV12_to_RGB24(_host_ptr(src0, np.uint8, px, "src0"), _host_ptr(src1, np.uint8, px // 4, "src1"),
                                  _host_ptr(src2, np.uint8, px // 4, "src2"),
                                  _host_ptr(dst_ori, np.uint8, 3 * px, "dst_ori", True), width, height)
+
+    def YV12_to_RGB24_multi(self, src0, src1, src2, dst_ori, width, height):
+        """lv_convert_host_multi: lists of per-picture arrays (the dialog's srcY[5], srcU[5], srcV[5], RGBbuf[5],
+        MainDlg.cpp:946-974); uploads, kernels and downloads of the pictures overlap, one wait at the end."""
+        n = len(src0)
+        if not (len(src1) == len(src2) == len(dst_ori) == n):
+            raise ValueError("YV12_to_RGB24_multi: the four lists must have the same length")
+        px = width * height
+        arr = lambda xs, nb, name, w=False: (C.c_void_p * n)(*[_host_ptr(a, np.uint8, nb, name, w) for a in xs])  # noqa: E731
+        capi.check(capi.lib().lv_convert_host_multi(arr(src0, px, "src0"), arr(src1, px // 4, "src1"), arr(src2, px // 4, "src2"),
+                                                    arr(dst_ori, 3 * px, "dst_ori", True), n, width, height),
+                   "lv_convert_host_multi")
 
     # the five methods the application never calls (Convert.h:25-30): same (in, out, w, h) convention, in place
     def _fmt(self, name, kind, inp, out, w, h):
@@ -95,7 +108,34 @@ def FrameDiff_MB(cur_y, ref_y, width, height, tol=DEFAULT_TOL, mb_thresh=DEFAULT
     return mask, mb_count, mb_map
 
 
-def _dev_ptr(t, dtype, numel, name, device):
+def FrameDiff_MB_multi(cur_y, ref_y, width, height, tol=DEFAULT_TOL, mb_thresh=DEFAULT_MB_THRESH, mask=None, mb_count=None,
+                       mb_map=None):
+    """lv_diff_host_multi: FrameDiff_MB over lists of pictures in one pipelined call.  Output lists are allocated when
+    not given; returns (mask, mb_count, mb_map) as lists of arrays."""
+    n = len(cur_y)
+    if len(ref_y) != n:
+        raise ValueError("FrameDiff_MB_multi: cur_y and ref_y must have the same length")
+    px = width * height
+    mbs = ((width + 15) // 16) * ((height + 15) // 16)
+    if mask is None:
+        mask = [np.empty(px, dtype=np.uint8) for _ in range(n)]
+    if mb_count is None:
+        mb_count = [np.empty(mbs, dtype=np.uint16) for _ in range(n)]
+    if mb_map is None:
+        mb_map = [np.empty(mbs, dtype=np.uint8) for _ in range(n)]
+    if n == 0 or width <= 0 or height <= 0:
+        return mask, mb_count, mb_map
+
+    def arr(xs, dt, nb, name, w=False):
+        return (C.c_void_p * n)(*[_host_ptr(a, dt, nb, name, w) for a in xs])
+    capi.check(capi.lib().lv_diff_host_multi(arr(cur_y, np.uint8, px, "cur_y"), arr(ref_y, np.uint8, px, "ref_y"), n, width, height,
+                                             int(tol), int(mb_thresh), arr(mask, np.uint8, px, "mask", True),
+                                             arr(mb_count, np.uint16, 2 * mbs, "mb_count", True),
+                                             arr(mb_map, np.uint8, mbs, "mb_map", True)), "lv_diff_host_multi")
+    return mask, mb_count, mb_map
+
+
+def _dev_ptr(t, dtype, numel, name, device, align=1):
     import torch
     if t is None:
         return None
@@ -107,6 +147,8 @@ def _dev_ptr(t, dtype, numel, name, device):
         raise ValueError(f"{name}: expected a contiguous {dtype} tensor")
     if t.numel() < numel:
         raise ValueError(f"{name}: needs {numel} elements, has {t.numel()}")
+    if t.data_ptr() % align:
+        raise ValueError(f"{name}: must be {align}-byte aligned (a slice at an odd offset?)")
     return t.data_ptr()
 
 
@@ -207,31 +249,73 @@ class Context:
         n = n_streams * n_frames
         d = self.device
         capi.check(capi.lib().lv_convert_diff_batch(
-            self._h, _dev_ptr(i420, torch.uint8, n * self.frame_bytes, "i420", d), first_stream, n_streams, n_frames,
-            _dev_ptr(out.get("bgr"), torch.uint8, n * self.bgr_bytes, "bgr", d),
+            self._h, _dev_ptr(i420, torch.uint8, n * self.frame_bytes, "i420", d, 16), first_stream, n_streams, n_frames,
+            _dev_ptr(out.get("bgr"), torch.uint8, n * self.bgr_bytes, "bgr", d, 16),
             _dev_ptr(out.get("mask_bits"), torch.int16, n * self.mask_units, "mask_bits", d),
-            _dev_ptr(out.get("mask_bytes"), torch.uint8, n * self.px, "mask_bytes", d),
+            _dev_ptr(out.get("mask_bytes"), torch.uint8, n * self.px, "mask_bytes", d, 16),
             _dev_ptr(out.get("mb_count"), torch.int16, n * self.mbs, "mb_count", d),
             _dev_ptr(out.get("mb_map"), torch.uint8, n * self.mbs, "mb_map", d),
             summary_ptr if summary_ptr is not None else _dev_ptr(out.get("summary"), torch.int32, n * 2, "summary", d),
             _stream_handle(cuda_stream)), "lv_convert_diff_batch")
 
+    def convert_diff_box_batch(self, i420, n_streams, n_frames, out, windows, boxes=None, first_stream=0, cuda_stream=None):
+        """The fused step with the object box of lib/JM/image.c:4818-4838 accumulated by the same launch (no mask in
+        memory).  windows: int32 CUDA tensor [n_streams*n_frames, n_objects, 4] = {x0, x1, y0, y1} inclusive; returns the
+        int32 CUDA tensor [n_streams*n_frames, n_objects, 4] = {min_x, max_x, min_y, max_y}.  out["bgr"] may be None."""
+        import torch
+        n, d = n_streams * n_frames, self.device
+        if windows.dim() != 3 or windows.shape[0] != n or windows.shape[2] != 4:
+            raise ValueError("windows: expected [n_streams*n_frames, n_objects, 4]")
+        n_obj = windows.shape[1]
+        if boxes is None:
+            boxes = torch.empty((n, n_obj, 4), dtype=torch.int32, device=torch.device("cuda", d))
+        capi.check(capi.lib().lv_convert_diff_box_batch(
+            self._h, _dev_ptr(i420, torch.uint8, n * self.frame_bytes, "i420", d, 16), first_stream, n_streams, n_frames,
+            _dev_ptr(out.get("bgr"), torch.uint8, n * self.bgr_bytes, "bgr", d, 16),
+            _dev_ptr(out.get("mb_count"), torch.int16, n * self.mbs, "mb_count", d),
+            _dev_ptr(out.get("mb_map"), torch.uint8, n * self.mbs, "mb_map", d),
+            _dev_ptr(out.get("summary"), torch.int32, n * 2, "summary", d),
+            _dev_ptr(windows, torch.int32, n * n_obj * 4, "windows", d, 16), n_obj,
+            _dev_ptr(boxes, torch.int32, n * n_obj * 4, "boxes", d, 16), _stream_handle(cuda_stream)),
+            "lv_convert_diff_box_batch")
+        return boxes
+
+    def object_windows(self, objects, hor_margin=8, ver_margin=8, cuda_stream=None):
+        """Windows {x0, x1, y0, y1} of objects {PosX, PosY, Width, Height} (int32 CUDA tensor [..., 4];
+        lib/JM/image.c:4786-4789, margins HOR/VER_DECODING_MARGIN = 8)."""
+        import torch
+        win = torch.empty_like(objects)
+        n = objects.numel() // 4
+        capi.check(capi.lib().lv_object_windows(self._h, _dev_ptr(objects, torch.int32, 4 * n, "objects", self.device, 16), n,
+                                                hor_margin, ver_margin, win.data_ptr(), _stream_handle(cuda_stream)),
+                   "lv_object_windows")
+        return win
+
+    def object_update(self, boxes, objects, cuda_stream=None):
+        """objects <- boxes under the reference's guard min < max (lib/JM/image.c:4840-4848); in place."""
+        import torch
+        n = objects.numel() // 4
+        capi.check(capi.lib().lv_object_update(self._h, _dev_ptr(boxes, torch.int32, 4 * n, "boxes", self.device, 16), n,
+                                               _dev_ptr(objects, torch.int32, 4 * n, "objects", self.device, 16),
+                                               _stream_handle(cuda_stream)), "lv_object_update")
+        return objects
+
     def convert_batch(self, i420, n_frames, bgr, cuda_stream=None):
         import torch
         d = self.device
         capi.check(capi.lib().lv_convert_batch(
-            self._h, _dev_ptr(i420, torch.uint8, n_frames * self.frame_bytes, "i420", d), n_frames,
-            _dev_ptr(bgr, torch.uint8, n_frames * self.bgr_bytes, "bgr", d), _stream_handle(cuda_stream)),
+            self._h, _dev_ptr(i420, torch.uint8, n_frames * self.frame_bytes, "i420", d, 16), n_frames,
+            _dev_ptr(bgr, torch.uint8, n_frames * self.bgr_bytes, "bgr", d, 16), _stream_handle(cuda_stream)),
             "lv_convert_batch")
 
     def diff_batch(self, cur_y, ref_y, n_frames, out, cuda_stream=None):
         import torch
         d = self.device
         capi.check(capi.lib().lv_diff_batch(
-            self._h, _dev_ptr(cur_y, torch.uint8, n_frames * self.px, "cur_y", d),
-            _dev_ptr(ref_y, torch.uint8, n_frames * self.px, "ref_y", d), n_frames,
+            self._h, _dev_ptr(cur_y, torch.uint8, n_frames * self.px, "cur_y", d, 16),
+            _dev_ptr(ref_y, torch.uint8, n_frames * self.px, "ref_y", d, 16), n_frames,
             _dev_ptr(out.get("mask_bits"), torch.int16, n_frames * self.mask_units, "mask_bits", d),
-            _dev_ptr(out.get("mask_bytes"), torch.uint8, n_frames * self.px, "mask_bytes", d),
+            _dev_ptr(out.get("mask_bytes"), torch.uint8, n_frames * self.px, "mask_bytes", d, 16),
             _dev_ptr(out.get("mb_count"), torch.int16, n_frames * self.mbs, "mb_count", d),
             _dev_ptr(out.get("mb_map"), torch.uint8, n_frames * self.mbs, "mb_map", d),
             _dev_ptr(out.get("summary"), torch.int32, n_frames * 2, "summary", d), _stream_handle(cuda_stream)),

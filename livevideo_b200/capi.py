@@ -23,6 +23,9 @@ SYMBOLS = {
     "YV12_to_YVU9": (None, [_vp, _vp, C.c_int, C.c_int]),
     "YV12_to_YUY2": (None, [_vp, _vp, C.c_int, C.c_int]),
     "FrameDiff_MB": (None, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "lv_convert_host_multi": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.c_int, C.c_int, C.c_int]),
+    "lv_diff_host_multi": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "lv_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "lv_destroy": (None, [_vp]),
     "lv_set_params": (C.c_int, [_vp, C.c_int, C.c_int]),
@@ -36,6 +39,9 @@ SYMBOLS = {
     "lv_reset_prev_luma": (C.c_int, [_vp, _vp]),
     "lv_convert_diff_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lv_convert_diff_batch_ex": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "lv_convert_diff_box_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
+    "lv_object_windows": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "lv_object_update": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "lv_convert_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "lv_diff_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lv_write_bks": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
@@ -74,6 +80,8 @@ SYMBOLS = {
     "lv_exchange_publish": (C.c_int, [_vp, C.c_uint64, _vp, C.c_int, _vp]),
     "lv_exchange_collect": (C.c_int, [_vp, C.c_uint64, _vp, _vp]),
     "lv_exchange_error": (C.c_int, [_vp]),
+    "lv_exchange_gate": (C.c_int, [_vp, _vp]),
+    "lv_exchange_wait_summary": (C.c_int, [_vp, C.c_uint64, _vp]),
     "lv_exchange_step": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    C.POINTER(C.c_uint64)]),
     "lv_exchange_flush": (C.c_int, [_vp]),

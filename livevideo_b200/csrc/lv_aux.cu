@@ -481,4 +481,45 @@ int launch_narrow(const Geom &g, const uint16_t *pic16, int n_frames, int size_x
     return launches;
 }
 
+// ---- object bookkeeping either side of the box ---------------------------------------------------------------------
+namespace {
+// lib/JM/image.h:23-24
+__device__ __forceinline__ int clip_x(int x, int w) { return x < 0 ? 0 : (x >= w ? w - 1 : x); }
+
+// window of an object: its last position +- half its size +- the decoding margin, clipped to the picture
+// (lib/JM/image.c:4786-4789; HOR/VER_DECODING_MARGIN = 8, lib/JM/global.h:119-120)
+__global__ void k_object_windows(const int4 *obj, int n, int w, int h, int hm, int vm, int4 *win)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 o = obj[i];      // PosX, PosY, Width, Height
+    win[i] = make_int4(clip_x(o.x - o.z / 2 - hm, w), clip_x(o.x + o.z / 2 + hm, w), clip_x(o.y - o.w / 2 - vm, h),
+                       clip_x(o.y + o.w / 2 + vm, h));
+}
+
+// position / size of the object from its box, only when the box is not degenerate (lib/JM/image.c:4840-4848)
+__global__ void k_object_update(const int4 *box, int n, int4 *obj)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 b = box[i];      // min_x, max_x, min_y, max_y
+    if (b.x < b.y && b.z < b.w) obj[i] = make_int4(b.x + (b.y - b.x) / 2, b.z + (b.w - b.z) / 2, b.y - b.x, b.w - b.z);
+}
+}  // namespace
+
+int launch_object_windows(int w, int h, const int *objects, int n, int hor_margin, int ver_margin, int *windows, cudaStream_t st)
+{
+    k_object_windows<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const int4 *>(objects), n, w, h, hor_margin, ver_margin,
+                                                       reinterpret_cast<int4 *>(windows));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+int launch_object_update(const int *boxes, int n, int *objects, cudaStream_t st)
+{
+    k_object_update<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const int4 *>(boxes), n, reinterpret_cast<int4 *>(objects));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
 }  // namespace lv

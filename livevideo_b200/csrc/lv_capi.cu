@@ -48,7 +48,8 @@ struct lv_ctx {
     int max_streams = 0;
     int tol = 20, mb_thresh = 0;
     uint8_t *state[2] = {nullptr, nullptr};   // ping-pong previous-luma planes, max_streams x px each
-    int cur = 0;                              // state[cur] holds the live previous luma
+    uint8_t *live = nullptr;                  // [max_streams] which of the two planes holds stream s's previous luma:
+                                              // per STREAM, so a step over streams [a,b) touches nobody else's state
     int ref_mode = 0;                         // LV_REF_PREVIOUS / LV_REF_STATIC
     uint64_t launches = 0;
     // host-step pipeline (created on first lv_step_host)
@@ -87,6 +88,16 @@ struct DeviceGuard {
 };
 
 bool geom_fast(int w, int h) { return w >= 16 && h >= 2 && w % 16 == 0 && h % 2 == 0; }
+
+// The tile kernels move 16-byte words (luma, BGR, byte mask, state) and 8-byte words (chroma); frame and plane sizes
+// are multiples of 16 bytes for every geometry they accept, so it is enough that each BASE pointer is 16-byte aligned.
+// A misaligned vector access would raise a sticky cudaErrorMisalignedAddress that kills the context: refuse instead.
+bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+int misaligned(const char *what)
+{
+    snprintf(g_err, sizeof g_err, "%s is not aligned as include/livevideo.h requires", what);
+    return LV_E_ARG;
+}
 
 void free_pipeline(lv_ctx *c)
 {
@@ -189,6 +200,11 @@ int lv_create(int device, int width, int height, int max_streams, int tol, int m
     c->mb_thresh = mb_thresh;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     const size_t bytes = c->g.px * (size_t)max_streams;
+    c->live = new (std::nothrow) uint8_t[max_streams]();
+    if (!c->live) {
+        delete c;
+        return LV_E_NOMEM;
+    }
     for (int i = 0; i < 2; i++) {
         e = cudaMalloc(&c->state[i], bytes);
         if (e == cudaSuccess) e = cudaMemset(c->state[i], 0, bytes);   // calloc'ed prev_frm, image.c:564-570
@@ -215,6 +231,7 @@ void lv_destroy(lv_ctx *c)
     if (c->s_upload) cudaStreamDestroy(c->s_upload);
     cudaFree(c->state[0]);
     cudaFree(c->state[1]);
+    delete[] c->live;
     delete c;
 }
 
@@ -245,7 +262,7 @@ int lv_set_prev_luma(lv_ctx *c, int stream, const uint8_t *y, int is_device, voi
     if (!c || !y || stream < 0 || stream >= c->max_streams) return LV_E_ARG;
     DeviceGuard guard(c->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    LV_CUDA(cudaMemcpyAsync(c->state[c->cur] + (size_t)stream * c->g.px, y, c->g.px,
+    LV_CUDA(cudaMemcpyAsync(c->state[c->live[stream]] + (size_t)stream * c->g.px, y, c->g.px,
                             is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     if (!is_device) LV_CUDA(cudaStreamSynchronize(st));
     return LV_OK;
@@ -256,7 +273,7 @@ int lv_get_prev_luma(lv_ctx *c, int stream, uint8_t *y, int is_device, void *cud
     if (!c || !y || stream < 0 || stream >= c->max_streams) return LV_E_ARG;
     DeviceGuard guard(c->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    LV_CUDA(cudaMemcpyAsync(y, c->state[c->cur] + (size_t)stream * c->g.px, c->g.px,
+    LV_CUDA(cudaMemcpyAsync(y, c->state[c->live[stream]] + (size_t)stream * c->g.px, c->g.px,
                             is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
     if (!is_device) LV_CUDA(cudaStreamSynchronize(st));
     return LV_OK;
@@ -266,7 +283,8 @@ int lv_reset_prev_luma(lv_ctx *c, void *cuda_stream)
 {
     if (!c) return LV_E_ARG;
     DeviceGuard guard(c->device);
-    LV_CUDA(cudaMemsetAsync(c->state[c->cur], 0, c->g.px * (size_t)c->max_streams, (cudaStream_t)cuda_stream));
+    LV_CUDA(cudaMemsetAsync(c->state[0], 0, c->g.px * (size_t)c->max_streams, (cudaStream_t)cuda_stream));
+    memset(c->live, 0, (size_t)c->max_streams);
     return LV_OK;
 }
 
@@ -278,54 +296,116 @@ int lv_convert_diff_batch(lv_ctx *c, const uint8_t *d_i420, int first_stream, in
                                     d_mb_map, d_summary, cuda_stream, 0);
 }
 
-int lv_convert_diff_batch_ex(lv_ctx *c, const uint8_t *d_i420, int first_stream, int n_streams, int n_frames,
-                             uint8_t *d_bgr, uint16_t *d_mask_bits, uint8_t *d_mask_bytes, uint16_t *d_mb_count,
-                             uint8_t *d_mb_map, uint32_t *d_summary, void *cuda_stream, int flags)
+}  // extern "C"
+
+namespace {
+int step_impl(lv_ctx *c, const uint8_t *d_i420, int first_stream, int n_streams, int n_frames, uint8_t *d_bgr,
+              uint16_t *d_mask_bits, uint8_t *d_mask_bytes, uint16_t *d_mb_count, uint8_t *d_mb_map, uint32_t *d_summary,
+              const int *d_windows, int n_objects, int *d_boxes, void *cuda_stream, int flags)
 {
     if (!c || !d_i420) return LV_E_ARG;
     if (n_streams < 0 || n_frames < 0 || first_stream < 0 || first_stream + n_streams > c->max_streams) return LV_E_ARG;
     if (!geom_fast(c->g.w, c->g.h)) return LV_E_SIZE;
+    if (!aligned(d_i420, 16)) return misaligned("d_i420 (16 bytes)");
+    if (!aligned(d_bgr, 16)) return misaligned("d_bgr (16 bytes)");
+    if (!aligned(d_mask_bytes, 16)) return misaligned("d_mask_bytes (16 bytes)");
+    if (!aligned(d_mask_bits, 2) || !aligned(d_mb_count, 2)) return misaligned("d_mask_bits / d_mb_count (2 bytes)");
+    if (!aligned(d_summary, 4)) return misaligned("d_summary (4 bytes)");
     if (n_streams == 0 || n_frames == 0) return LV_OK;
     DeviceGuard guard(c->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (d_summary && !(flags & LV_STEP_SUMMARY_PREZEROED))
+    if (d_boxes) {
+        // one small kernel zeroes the summary (in place of the memset) and sets every box to its initial value
+        int rc = launch_result(lv::launch_step_init((flags & LV_STEP_SUMMARY_PREZEROED) ? nullptr : d_summary,
+                                                    (size_t)n_streams * n_frames, d_windows, d_boxes, n_objects, st), c->launches);
+        if (rc != LV_OK) return rc;
+    } else if (d_summary && !(flags & LV_STEP_SUMMARY_PREZEROED))
         LV_CUDA(cudaMemsetAsync(d_summary, 0, sizeof(uint32_t) * 2 * (size_t)n_streams * n_frames, st));
-    lv::StepArgs a{};
-    a.g = c->g;
-    a.i420 = d_i420;
-    a.state_in = c->state[c->cur] + (size_t)first_stream * c->g.px;
-    a.state_out = c->state[c->cur ^ 1] + (size_t)first_stream * c->g.px;
-    a.n_streams = n_streams; a.n_frames = n_frames;
-    a.tol = c->tol; a.mb_thresh = c->mb_thresh;
-    a.bgr = d_bgr; a.mask_bits = d_mask_bits; a.mask_bytes = d_mask_bytes;
-    a.mb_count = d_mb_count; a.mb_map = d_mb_map; a.summary = d_summary;
-    if (c->ref_mode == LV_REF_STATIC) {
+    const lv::Geom &g = c->g;
+    const size_t mbs = (size_t)g.mb_w * g.mb_h;
+    const bool is_static = c->ref_mode == LV_REF_STATIC;
+    // One launch per run of streams whose previous luma lives in the same plane of the ping-pong pair (a launch reads
+    // state[p] and writes state[p ^ 1], so it never reads a plane it rewrites).  Streams that always step together --
+    // the whole context, or the same sub-range every time -- form ONE run; nothing is ever copied between the planes.
+    for (int s0 = 0; s0 < n_streams;) {
+        const int p = c->live[first_stream + s0];
+        int s1 = s0 + 1;
+        while (s1 < n_streams && c->live[first_stream + s1] == p) s1++;
+        const size_t f0 = (size_t)s0 * n_frames;
+        lv::StepArgs a{};
+        a.g = g;
+        a.i420 = d_i420 + f0 * g.frame;
+        a.state_in = c->state[p] + (size_t)(first_stream + s0) * g.px;
         // static background (MainDlg.cpp:238-246): the stored plane is the reference of every frame and stays as it is
-        a.static_ref = 1;
-        a.state_out = nullptr;
-        return launch_result(lv::launch_step(a, st), c->launches);
+        a.state_out = is_static ? nullptr : c->state[p ^ 1] + (size_t)(first_stream + s0) * g.px;
+        a.static_ref = is_static ? 1 : 0;
+        a.n_streams = s1 - s0; a.n_frames = n_frames;
+        a.tol = c->tol; a.mb_thresh = c->mb_thresh;
+        a.bgr = d_bgr ? d_bgr + f0 * 3 * g.px : nullptr;
+        a.mask_bits = d_mask_bits ? d_mask_bits + f0 * g.h * g.units : nullptr;
+        a.mask_bytes = d_mask_bytes ? d_mask_bytes + f0 * g.px : nullptr;
+        a.mb_count = d_mb_count ? d_mb_count + f0 * mbs : nullptr;
+        a.mb_map = d_mb_map ? d_mb_map + f0 * mbs : nullptr;
+        a.summary = d_summary ? d_summary + 2 * f0 : nullptr;
+        if (d_boxes) {
+            a.windows = d_windows + 4 * f0 * n_objects;
+            a.boxes = d_boxes + 4 * f0 * n_objects;
+            a.n_obj = n_objects;
+        }
+        const int rc = launch_result(lv::launch_step(a, st), c->launches);
+        if (rc != LV_OK) return rc;
+        if (!is_static)
+            for (int s = s0; s < s1; s++) c->live[first_stream + s] ^= 1;
+        s0 = s1;
     }
-    int rc = launch_result(lv::launch_step(a, st), c->launches);
-    if (rc != LV_OK) return rc;
-    // Streams outside [first_stream, first_stream+n_streams) keep their state: carry it over to the
-    // plane set that becomes live.  (Whole-context batches, the common case, copy nothing.)
-    if (first_stream > 0)
-        LV_CUDA(cudaMemcpyAsync(c->state[c->cur ^ 1], c->state[c->cur], (size_t)first_stream * c->g.px,
-                                cudaMemcpyDeviceToDevice, st));
-    if (first_stream + n_streams < c->max_streams) {
-        const size_t off = (size_t)(first_stream + n_streams) * c->g.px;
-        LV_CUDA(cudaMemcpyAsync(c->state[c->cur ^ 1] + off, c->state[c->cur] + off,
-                                (size_t)(c->max_streams - first_stream - n_streams) * c->g.px,
-                                cudaMemcpyDeviceToDevice, st));
-    }
-    c->cur ^= 1;
     return LV_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int lv_convert_diff_batch_ex(lv_ctx *c, const uint8_t *d_i420, int first_stream, int n_streams, int n_frames,
+                             uint8_t *d_bgr, uint16_t *d_mask_bits, uint8_t *d_mask_bytes, uint16_t *d_mb_count,
+                             uint8_t *d_mb_map, uint32_t *d_summary, void *cuda_stream, int flags)
+{
+    return step_impl(c, d_i420, first_stream, n_streams, n_frames, d_bgr, d_mask_bits, d_mask_bytes, d_mb_count, d_mb_map,
+                     d_summary, nullptr, 0, nullptr, cuda_stream, flags);
+}
+
+int lv_convert_diff_box_batch(lv_ctx *c, const uint8_t *d_i420, int first_stream, int n_streams, int n_frames, uint8_t *d_bgr,
+                              uint16_t *d_mb_count, uint8_t *d_mb_map, uint32_t *d_summary, const int *d_windows,
+                              int n_objects, int *d_boxes, void *cuda_stream)
+{
+    if (!d_windows || !d_boxes || n_objects < 1 || n_objects > LV_MAX_OBJECTS) return LV_E_ARG;
+    if (!aligned(d_windows, 16) || !aligned(d_boxes, 16)) return misaligned("d_windows / d_boxes (16 bytes)");
+    return step_impl(c, d_i420, first_stream, n_streams, n_frames, d_bgr, nullptr, nullptr, d_mb_count, d_mb_map, d_summary,
+                     d_windows, n_objects, d_boxes, cuda_stream, 0);
+}
+
+int lv_object_windows(lv_ctx *c, const int *d_objects, int n, int hor_margin, int ver_margin, int *d_windows, void *cuda_stream)
+{
+    if (!c || !d_objects || !d_windows || n < 0) return LV_E_ARG;
+    if (!aligned(d_objects, 16) || !aligned(d_windows, 16)) return misaligned("d_objects / d_windows (16 bytes)");
+    if (n == 0) return LV_OK;
+    DeviceGuard guard(c->device);
+    return launch_result(lv::launch_object_windows(c->g.w, c->g.h, d_objects, n, hor_margin, ver_margin, d_windows,
+                                                   (cudaStream_t)cuda_stream), c->launches);
+}
+
+int lv_object_update(lv_ctx *c, const int *d_boxes, int n, int *d_objects, void *cuda_stream)
+{
+    if (!c || !d_boxes || !d_objects || n < 0) return LV_E_ARG;
+    if (!aligned(d_boxes, 16) || !aligned(d_objects, 16)) return misaligned("d_boxes / d_objects (16 bytes)");
+    if (n == 0) return LV_OK;
+    DeviceGuard guard(c->device);
+    return launch_result(lv::launch_object_update(d_boxes, n, d_objects, (cudaStream_t)cuda_stream), c->launches);
 }
 
 int lv_convert_batch(lv_ctx *c, const uint8_t *d_i420, int n_frames, uint8_t *d_bgr, void *cuda_stream)
 {
     if (!c || !d_i420 || !d_bgr || n_frames < 0) return LV_E_ARG;
     if (!geom_fast(c->g.w, c->g.h)) return LV_E_SIZE;
+    if (!aligned(d_i420, 16) || !aligned(d_bgr, 16)) return misaligned("d_i420 / d_bgr (16 bytes)");
     if (n_frames == 0) return LV_OK;
     DeviceGuard guard(c->device);
     return launch_result(lv::launch_convert(c->g, d_i420, n_frames, d_bgr, (cudaStream_t)cuda_stream), c->launches);
@@ -337,6 +417,10 @@ int lv_diff_batch(lv_ctx *c, const uint8_t *d_cur_y, const uint8_t *d_ref_y, int
 {
     if (!c || !d_cur_y || !d_ref_y || n_frames < 0) return LV_E_ARG;
     if (!geom_fast(c->g.w, c->g.h)) return LV_E_SIZE;
+    if (!aligned(d_cur_y, 16) || !aligned(d_ref_y, 16) || !aligned(d_mask_bytes, 16))
+        return misaligned("d_cur_y / d_ref_y / d_mask_bytes (16 bytes)");
+    if (!aligned(d_mask_bits, 2) || !aligned(d_mb_count, 2) || !aligned(d_summary, 4))
+        return misaligned("d_mask_bits / d_mb_count (2 bytes) / d_summary (4 bytes)");
     if (n_frames == 0) return LV_OK;
     DeviceGuard guard(c->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -354,6 +438,7 @@ int lv_write_bks(lv_ctx *c, const uint8_t *d_cur, const uint8_t *d_bkd, int n_fr
 {
     if (!c || !d_cur || !d_bkd || !d_out || n_frames < 0 || tol < 0 || tol > 255) return LV_E_ARG;
     if (d_obj_bits && c->g.w % 16 != 0) return LV_E_SIZE;
+    if (!aligned(d_obj_bits, 2)) return misaligned("d_obj_bits (2 bytes)");   // the frames themselves may sit anywhere
     if (n_frames == 0) return LV_OK;
     DeviceGuard guard(c->device);
     return launch_result(lv::launch_write_bks(c->g, d_cur, d_bkd, n_frames, tol, d_out, d_obj_bits, (cudaStream_t)cuda_stream),
@@ -540,19 +625,21 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
     const size_t mbs = (size_t)g.mb_w * g.mb_h, units = (size_t)g.units * g.h;
 
     // chunk = cf frames of every stream; aim at ~LV_HOST_CHUNK_MB MiB of input per chunk, at least 1 frame
-    static size_t chunk_bytes = 0;
-    if (!chunk_bytes) {
-        const char *e = getenv("LV_HOST_CHUNK_MB");
+    auto env_mb = [](const char *name, long dflt, long max) -> size_t {
+        const char *e = getenv(name);
         const long mb = e ? atol(e) : 0;
-        chunk_bytes = (size_t)(mb > 0 && mb <= 1024 ? mb : LV_HOST_CHUNK_MB_DEFAULT) << 20;
-    }
+        return (size_t)(mb > 0 && mb <= max ? mb : dflt) << 20;
+    };
+    const size_t chunk_bytes = env_mb("LV_HOST_CHUNK_MB", LV_HOST_CHUNK_MB_DEFAULT, 1024);
     const size_t in_frame = pic ? pic->samples * sizeof(uint16_t) : g.frame;     // host bytes per frame
     int cf = (int)(chunk_bytes / (in_frame * (size_t)n_streams));
     if (cf < 1) cf = 1;
     if (cf > n_frames) cf = n_frames;
-    // a slot must hold one chunk; streams are cut too if even one frame of all streams is too large
+    // a slot must hold one chunk (at most LV_HOST_SLOT_MB MiB of input, default 256): streams are cut too when even one
+    // frame of all streams is larger.  Streams keep their state independently, so a cut by streams costs nothing.
     int cs = n_streams;
-    const size_t cap_frames = ((size_t)256 << 20) / g.frame > 0 ? ((size_t)256 << 20) / g.frame : 1;
+    const size_t slot_bytes = env_mb("LV_HOST_SLOT_MB", 256, 16384);
+    const size_t cap_frames = slot_bytes / g.frame > 0 ? slot_bytes / g.frame : 1;
     if ((size_t)cs * cf > cap_frames) { cf = 1; if ((size_t)cs > cap_frames) cs = (int)cap_frames; }
     int rc = ensure_pipeline(c, cs * cf);
     if (rc != LV_OK) return rc;
@@ -560,6 +647,36 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
         rc = ensure_pic_slots(c, pic->samples * (size_t)cs * cf);
         if (rc != LV_OK) return rc;
     }
+
+    // A chunk is `ns` runs of `nt` consecutive frames, `n_frames` frames apart in the host batch.  One strided copy moves
+    // it when both pitches fit the device's limit (cudaMemcpy2DAsync rejects larger ones: 2 GiB - 1 on B200, i.e. 87
+    // frames of 4K BGR); a single run is one plain copy; otherwise one plain copy per stream.
+    int max_pitch = 0;
+    cudaDeviceGetAttribute(&max_pitch, cudaDevAttrMaxPitch, c->device);
+    auto move = [&](void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, int rows, cudaMemcpyKind kind,
+                    cudaStream_t stm) -> cudaError_t {
+        if (rows == 1 || (dpitch == width && spitch == width)) return cudaMemcpyAsync(dst, src, width * (size_t)rows, kind, stm);
+        if (dpitch <= (size_t)max_pitch && spitch <= (size_t)max_pitch) return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, (size_t)rows, kind, stm);
+        for (int r = 0; r < rows; r++) {
+            cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t *>(dst) + (size_t)r * dpitch, static_cast<const uint8_t *>(src) + (size_t)r * spitch,
+                                            width, kind, stm);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    // any failure inside the loop: the copies already enqueued still read / write the caller's host buffers -- drain the
+    // three streams before handing the buffers back
+    auto bail = [&](int code) -> int {
+        cudaStreamSynchronize(c->s_copy_in);
+        cudaStreamSynchronize(c->s_compute);
+        cudaStreamSynchronize(c->s_copy_out);
+        return code;
+    };
+#define LV_PIPE(call)                                                  \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) return bail(cuda_fail(e_, #call));      \
+    } while (0)
 
     int k = 0;
     for (int s0 = 0; s0 < n_streams; s0 += cs) {
@@ -569,57 +686,47 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
             const int slot = k % lv_ctx::kSlots;
             // the slot's previous download must have drained before its buffers are reused
             if (k >= lv_ctx::kSlots) {
-                LV_CUDA(cudaStreamWaitEvent(c->s_copy_in, c->ev_k[slot], 0));
-                LV_CUDA(cudaStreamWaitEvent(c->s_compute, c->ev_out[slot], 0));
+                LV_PIPE(cudaStreamWaitEvent(c->s_copy_in, c->ev_k[slot], 0));
+                LV_PIPE(cudaStreamWaitEvent(c->s_compute, c->ev_out[slot], 0));
             }
-            // H2D: frames t0..t0+nt of stream s are contiguous in the host batch and the streams are n_frames frames
-            // apart: ONE strided copy for the whole chunk (32 streams x 1 frame is one call, not 32)
-            {
-                const size_t hf = (size_t)s0 * n_frames + t0;
-                cudaError_t up;
-                if (pic)
-                    up = cudaMemcpy2DAsync(c->d_pic[slot], (size_t)nt * pic->samples * sizeof(uint16_t),
-                                           pic->h_pic16 + hf * pic->samples, (size_t)n_frames * pic->samples * sizeof(uint16_t),
-                                           (size_t)nt * pic->samples * sizeof(uint16_t), (size_t)ns, cudaMemcpyHostToDevice,
-                                           c->s_copy_in);
-                else
-                    up = cudaMemcpy2DAsync(c->d_in[slot], (size_t)nt * g.frame, h_i420 + hf * g.frame, (size_t)n_frames * g.frame,
-                                           (size_t)nt * g.frame, (size_t)ns, cudaMemcpyHostToDevice, c->s_copy_in);
-                LV_CUDA(up);
-            }
-            LV_CUDA(cudaEventRecord(c->ev_in[slot], c->s_copy_in));
-            LV_CUDA(cudaStreamWaitEvent(c->s_compute, c->ev_in[slot], 0));
+            const size_t hf = (size_t)s0 * n_frames + t0;
+            if (pic)
+                LV_PIPE(move(c->d_pic[slot], (size_t)nt * pic->samples * sizeof(uint16_t), pic->h_pic16 + hf * pic->samples,
+                             (size_t)n_frames * pic->samples * sizeof(uint16_t), (size_t)nt * pic->samples * sizeof(uint16_t), ns,
+                             cudaMemcpyHostToDevice, c->s_copy_in));
+            else
+                LV_PIPE(move(c->d_in[slot], (size_t)nt * g.frame, h_i420 + hf * g.frame, (size_t)n_frames * g.frame,
+                             (size_t)nt * g.frame, ns, cudaMemcpyHostToDevice, c->s_copy_in));
+            LV_PIPE(cudaEventRecord(c->ev_in[slot], c->s_copy_in));
+            LV_PIPE(cudaStreamWaitEvent(c->s_compute, c->ev_in[slot], 0));
             if (pic) {     // img2buf + write_out_picture on the device: 16-bit planes -> the slot's tight I420 frames
                 rc = launch_result(lv::launch_narrow(g, c->d_pic[slot], ns * nt, pic->size_x, pic->size_y, pic->crop_left,
                                                      pic->crop_top, c->d_in[slot], c->s_compute), c->launches);
-                if (rc != LV_OK) return rc;
+                if (rc != LV_OK) return bail(rc);
             }
             rc = lv_convert_diff_batch(c, c->d_in[slot], first_stream + s0, ns, nt, h_bgr ? c->d_bgr[slot] : nullptr,
                                        h_mask_bits ? c->d_bits[slot] : nullptr, nullptr,
                                        h_mb_count ? c->d_cnt[slot] : nullptr, h_mb_map ? c->d_map[slot] : nullptr,
                                        h_summary ? c->d_sum[slot] : nullptr, c->s_compute);
-            if (rc != LV_OK) return rc;
-            LV_CUDA(cudaEventRecord(c->ev_k[slot], c->s_compute));
-            LV_CUDA(cudaStreamWaitEvent(c->s_copy_out, c->ev_k[slot], 0));
-            {
-                // D2H: the same strided shape per output (width = this chunk's nt frames of one stream, height = streams)
-                const size_t hf = (size_t)s0 * n_frames + t0;
-                auto down = [&](void *h_base, const void *d_base, size_t bytes_per_frame) -> cudaError_t {
-                    return cudaMemcpy2DAsync(static_cast<uint8_t *>(h_base) + hf * bytes_per_frame, (size_t)n_frames * bytes_per_frame,
-                                             d_base, (size_t)nt * bytes_per_frame, (size_t)nt * bytes_per_frame, (size_t)ns,
-                                             cudaMemcpyDeviceToHost, c->s_copy_out);
-                };
-                if (h_bgr) LV_CUDA(down(h_bgr, c->d_bgr[slot], 3 * g.px));
-                if (h_mask_bits) LV_CUDA(down(h_mask_bits, c->d_bits[slot], sizeof(uint16_t) * units));
-                if (h_mb_count) LV_CUDA(down(h_mb_count, c->d_cnt[slot], sizeof(uint16_t) * mbs));
-                if (h_mb_map) LV_CUDA(down(h_mb_map, c->d_map[slot], mbs));
-                if (h_summary) LV_CUDA(down(h_summary, c->d_sum[slot], sizeof(uint32_t) * 2));
-            }
-            LV_CUDA(cudaEventRecord(c->ev_out[slot], c->s_copy_out));
+            if (rc != LV_OK) return bail(rc);
+            LV_PIPE(cudaEventRecord(c->ev_k[slot], c->s_compute));
+            LV_PIPE(cudaStreamWaitEvent(c->s_copy_out, c->ev_k[slot], 0));
+            // D2H: the same strided shape per output (width = this chunk's nt frames of one stream, rows = streams)
+            auto down = [&](void *h_base, const void *d_base, size_t bytes_per_frame) -> cudaError_t {
+                return move(static_cast<uint8_t *>(h_base) + hf * bytes_per_frame, (size_t)n_frames * bytes_per_frame, d_base,
+                            (size_t)nt * bytes_per_frame, (size_t)nt * bytes_per_frame, ns, cudaMemcpyDeviceToHost, c->s_copy_out);
+            };
+            if (h_bgr) LV_PIPE(down(h_bgr, c->d_bgr[slot], 3 * g.px));
+            if (h_mask_bits) LV_PIPE(down(h_mask_bits, c->d_bits[slot], sizeof(uint16_t) * units));
+            if (h_mb_count) LV_PIPE(down(h_mb_count, c->d_cnt[slot], sizeof(uint16_t) * mbs));
+            if (h_mb_map) LV_PIPE(down(h_mb_map, c->d_map[slot], mbs));
+            if (h_summary) LV_PIPE(down(h_summary, c->d_sum[slot], sizeof(uint32_t) * 2));
+            LV_PIPE(cudaEventRecord(c->ev_out[slot], c->s_copy_out));
         }
     }
     LV_CUDA(cudaStreamSynchronize(c->s_copy_out));
     LV_CUDA(cudaStreamSynchronize(c->s_compute));
+#undef LV_PIPE
     return LV_OK;
 }
 }  // namespace
@@ -800,6 +907,182 @@ void FrameDiff_MB(const unsigned char *cur_y, const unsigned char *ref_y, int wi
     if (mb_map && e == cudaSuccess) e = cudaMemcpyAsync(mb_map, dmap, mbs, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { cuda_fail(e, "D2H"); legacy_die(fn, "copy failed"); }
+}
+
+// ---- several pictures per call: the reference's real call pattern -------------------------------------------------
+// CMainDlg::DisplayPic converts FIVE pictures back to back (MainDlg.cpp:946-974: srcY[i], srcU[i], srcV[i] -> RGBbuf[i]).
+// One synchronous call per picture serialises H2D -> kernel -> D2H five times; here the upload of picture i+1, the
+// kernel of picture i and the download of picture i-1 run on three streams and the host waits once, at the end.
+}  // extern "C"
+
+namespace {
+
+struct MultiPipe {
+    static const int kSlots = 3;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
+    LegacyBuf in[kSlots], out[kSlots];
+    bool ready = false;
+    int init()
+    {
+        if (ready) return LV_OK;
+        LV_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        LV_CUDA(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+        LV_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < kSlots; i++) {
+            LV_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            LV_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+            LV_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+        }
+        ready = true;
+        return LV_OK;
+    }
+    int drain(int code)
+    {
+        if (s_in) cudaStreamSynchronize(s_in);
+        if (s_k) cudaStreamSynchronize(s_k);
+        if (s_out) cudaStreamSynchronize(s_out);
+        return code;
+    }
+};
+thread_local MultiPipe t_pipe;
+
+// the per-thread device of the legacy entries, without the abort-on-failure of LegacyScope
+int multi_scope(DeviceGuard *&guard)
+{
+    if (t_device < 0) {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) {
+            cuda_fail(cudaGetLastError(), "cudaGetDevice");
+            return LV_E_NODEVICE;
+        }
+        t_device = d;
+    }
+    guard = new (std::nothrow) DeviceGuard(t_device);
+    if (!guard) return LV_E_NOMEM;
+    if (!guard->ok) {
+        cuda_fail(cudaGetLastError(), "cudaSetDevice");
+        return LV_E_NODEVICE;
+    }
+    return t_pipe.init();
+}
+struct GuardOwner {
+    DeviceGuard *g = nullptr;
+    ~GuardOwner() { delete g; }
+};
+
+#define LV_MP(call)                                                            \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) return P.drain(cuda_fail(e_, #call));           \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int lv_convert_host_multi(const unsigned char *const *src0, const unsigned char *const *src1, const unsigned char *const *src2,
+                          unsigned char *const *dst_ori, int n, int width, int height)
+{
+    if (n < 0 || (n > 0 && (!src0 || !src1 || !src2 || !dst_ori))) return LV_E_ARG;
+    for (int i = 0; i < n; i++)
+        if (!src0[i] || !src1[i] || !src2[i] || !dst_ori[i]) return LV_E_ARG;
+    if (n == 0 || width <= 0 || height <= 0) return LV_OK;
+    if (width % 4 != 0 || height % 2 != 0) return LV_E_SIZE;
+    GuardOwner go;
+    int rc = multi_scope(go.g);
+    if (rc != LV_OK) return rc;
+    MultiPipe &P = t_pipe;
+    const size_t px = (size_t)width * height;
+    const bool fast = geom_fast(width, height);
+    const lv::Geom g = lv::make_geom(width, height);
+    for (int i = 0; i < n; i++) {
+        const int slot = i % MultiPipe::kSlots;
+        uint8_t *din = P.in[slot].get(px + px / 2), *dout = P.out[slot].get(3 * px);
+        if (!din || !dout) return P.drain(LV_E_NOMEM);
+        if (i >= MultiPipe::kSlots) {
+            LV_MP(cudaStreamWaitEvent(P.s_in, P.ev_k[slot], 0));     // the kernel that read this slot's input
+            LV_MP(cudaStreamWaitEvent(P.s_k, P.ev_out[slot], 0));    // the download of this slot's output
+        }
+        LV_MP(cudaMemcpyAsync(din, src0[i], px, cudaMemcpyHostToDevice, P.s_in));
+        LV_MP(cudaMemcpyAsync(din + px, src1[i], px / 4, cudaMemcpyHostToDevice, P.s_in));
+        LV_MP(cudaMemcpyAsync(din + px + px / 4, src2[i], px / 4, cudaMemcpyHostToDevice, P.s_in));
+        LV_MP(cudaEventRecord(P.ev_in[slot], P.s_in));
+        LV_MP(cudaStreamWaitEvent(P.s_k, P.ev_in[slot], 0));
+        const int r = fast ? lv::launch_convert(g, din, 1, dout, P.s_k)
+                           : lv::launch_convert_generic(width, height, din, din + px, din + px + px / 4, dout, P.s_k);
+        if (r < 0) return P.drain(cuda_fail((cudaError_t)(-r), "kernel launch"));
+        LV_MP(cudaEventRecord(P.ev_k[slot], P.s_k));
+        LV_MP(cudaStreamWaitEvent(P.s_out, P.ev_k[slot], 0));
+        LV_MP(cudaMemcpyAsync(dst_ori[i], dout, 3 * px, cudaMemcpyDeviceToHost, P.s_out));
+        LV_MP(cudaEventRecord(P.ev_out[slot], P.s_out));
+    }
+    LV_MP(cudaStreamSynchronize(P.s_out));
+    return LV_OK;
+}
+
+int lv_diff_host_multi(const unsigned char *const *cur_y, const unsigned char *const *ref_y, int n, int width, int height, int tol,
+                       int mb_thresh, unsigned char *const *mask, unsigned short *const *mb_count, unsigned char *const *mb_map)
+{
+    if (n < 0 || (n > 0 && (!cur_y || !ref_y))) return LV_E_ARG;
+    for (int i = 0; i < n; i++)
+        if (!cur_y[i] || !ref_y[i]) return LV_E_ARG;
+    if (n == 0 || width <= 0 || height <= 0) return LV_OK;
+    if (tol < 0) tol = -1;
+    if (tol > 255) tol = 255;
+    GuardOwner go;
+    int rc = multi_scope(go.g);
+    if (rc != LV_OK) return rc;
+    MultiPipe &P = t_pipe;
+    const size_t px = (size_t)width * height, pxa = (px + 15) & ~(size_t)15;
+    const int mb_w = (width + 15) / 16, mb_h = (height + 15) / 16;
+    const size_t mbs = (size_t)mb_w * mb_h;
+    const size_t off_cnt = pxa, off_map = off_cnt + ((2 * mbs + 15) & ~(size_t)15);
+    const bool fast = geom_fast(width, height) && tol >= 0;
+    const lv::Geom g = lv::make_geom(width, height);
+    for (int i = 0; i < n; i++) {
+        const int slot = i % MultiPipe::kSlots, pslot = (i + MultiPipe::kSlots - 1) % MultiPipe::kSlots;
+        uint8_t *din = P.in[slot].get(2 * pxa), *dout = P.out[slot].get(off_map + mbs);
+        if (!din || !dout) return P.drain(LV_E_NOMEM);
+        // a sequence differenced against its own previous picture (ref_y[i] == cur_y[i-1], the prev_frm <- curr_frm of
+        // lib/JM/image.c:1553-1561) uploads every plane once: the previous slot's current plane is this one's reference
+        const bool chained = i > 0 && ref_y[i] == cur_y[i - 1];
+        if (i >= MultiPipe::kSlots) {
+            LV_MP(cudaStreamWaitEvent(P.s_in, P.ev_k[slot], 0));
+            LV_MP(cudaStreamWaitEvent(P.s_k, P.ev_out[slot], 0));
+        }
+        if (i >= MultiPipe::kSlots - 1)       // picture i-2's kernel may have read this slot's current plane as ITS reference
+            LV_MP(cudaStreamWaitEvent(P.s_in, P.ev_k[(i + 1) % MultiPipe::kSlots], 0));
+        LV_MP(cudaMemcpyAsync(din, cur_y[i], px, cudaMemcpyHostToDevice, P.s_in));
+        const uint8_t *dref = chained ? P.in[pslot].d : din + pxa;
+        if (!chained) LV_MP(cudaMemcpyAsync(din + pxa, ref_y[i], px, cudaMemcpyHostToDevice, P.s_in));
+        LV_MP(cudaEventRecord(P.ev_in[slot], P.s_in));
+        LV_MP(cudaStreamWaitEvent(P.s_k, P.ev_in[slot], 0));
+        uint8_t *m = mask ? mask[i] : nullptr;
+        unsigned short *hc = mb_count ? mb_count[i] : nullptr;
+        uint8_t *hm = mb_map ? mb_map[i] : nullptr;
+        uint8_t *dmask = m ? dout : nullptr;
+        uint16_t *dcnt = reinterpret_cast<uint16_t *>(dout + off_cnt);
+        uint8_t *dmap = dout + off_map;
+        int r;
+        if (fast) {
+            lv::DiffArgs a{};
+            a.g = g; a.cur_y = din; a.ref_y = dref; a.n_frames = 1;
+            a.tol = tol; a.mb_thresh = mb_thresh; a.mask_bytes = dmask; a.mb_count = dcnt; a.mb_map = dmap;
+            r = lv::launch_diff(a, P.s_k);
+        } else {
+            r = lv::launch_diff_generic(width, height, din, dref, tol, mb_thresh, dmask, dcnt, dmap, P.s_k);
+        }
+        if (r < 0) return P.drain(cuda_fail((cudaError_t)(-r), "kernel launch"));
+        LV_MP(cudaEventRecord(P.ev_k[slot], P.s_k));
+        LV_MP(cudaStreamWaitEvent(P.s_out, P.ev_k[slot], 0));
+        if (m) LV_MP(cudaMemcpyAsync(m, dmask, px, cudaMemcpyDeviceToHost, P.s_out));
+        if (hc) LV_MP(cudaMemcpyAsync(hc, dcnt, 2 * mbs, cudaMemcpyDeviceToHost, P.s_out));
+        if (hm) LV_MP(cudaMemcpyAsync(hm, dmap, mbs, cudaMemcpyDeviceToHost, P.s_out));
+        LV_MP(cudaEventRecord(P.ev_out[slot], P.s_out));
+    }
+    LV_MP(cudaStreamSynchronize(P.s_out));
+    return LV_OK;
 }
 
 }  // extern "C"

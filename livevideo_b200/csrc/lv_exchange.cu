@@ -12,8 +12,11 @@
 //                                            word and its own sequence number, so the receiver needs no flag behind a
 //                                            fence -- a word has arrived when its upper half says k+1
 //     ack  [world]                      u32   ack[r] == number of steps rank r has collected (retired)
-//     err                               u32   set when a wait gave up (a wait never spins forever: a hung GPU is worse)
+//     gate [world]                      u32   gate[r] == number of lv_exchange_gate calls rank r has reached
+//     err                               u32   set when a wait gave up (a wait never spins forever: a hung GPU is worse);
+//                                             mirrored into a host-mapped word so the host reads it without a copy
 //
+//   The sequence number of step k is (k mod (2^32 - 1)) + 1: never 0 (0 = "nothing has arrived"), for any 64-bit k.
 //   publish(k): wait (local reads) until every rank has retired step k-depth, then store the block, fire and forget.
 //   collect(k): spin on LOCAL memory until every word of ring slot k % depth carries k+1, copy the values out, then
 //               store ack = k+1 into every peer (the loads have returned by then; nothing to fence).
@@ -40,7 +43,7 @@
 namespace {
 
 constexpr int kMaxWorld = 32;
-constexpr unsigned long long kSpinLimitNs = 4000000000ull;   // a wait gives up after 4 s and raises err
+constexpr unsigned long long kSpinLimitNs = 4000000000ull;   // a KERNEL gives up 4 s after it started and raises err
 
 thread_local char x_err[256] = "";
 
@@ -59,7 +62,8 @@ struct Layout {
     int world, depth, slot_words;
     __host__ __device__ size_t data_words64() const { return (size_t)depth * world * slot_words; }
     __host__ __device__ size_t ack_off32() const { return 2 * data_words64(); }                  // in u32 words
-    __host__ __device__ size_t err_off32() const { return ack_off32() + (size_t)world; }
+    __host__ __device__ size_t gate_off32() const { return ack_off32() + (size_t)world; }
+    __host__ __device__ size_t err_off32() const { return gate_off32() + (size_t)world; }
     __host__ __device__ size_t bytes() const { return ((err_off32() + 1) * 4 + 15) & ~(size_t)15; }
 };
 
@@ -97,41 +101,74 @@ __device__ __forceinline__ uint32_t *ack_of(unsigned long long *buf, const Layou
 {
     return reinterpret_cast<uint32_t *>(buf) + L.ack_off32();
 }
+__device__ __forceinline__ uint32_t *gate_of(unsigned long long *buf, const Layout &L)
+{
+    return reinterpret_cast<uint32_t *>(buf) + L.gate_off32();
+}
 __device__ __forceinline__ uint32_t *err_of(unsigned long long *buf, const Layout &L)
 {
     return reinterpret_cast<uint32_t *>(buf) + L.err_off32();
 }
+__host__ __device__ __forceinline__ uint32_t seq_of(unsigned long long step)
+{
+    return (uint32_t)(step % 0xffffffffull) + 1u;      // 1 .. 2^32-1, never the "empty" value 0
+}
+
+// One deadline per kernel: `ok` (shared memory) drops to 0 when ANY thread of the block has waited past t0 + 4 s, and
+// every spin of every thread reads it, so a dead peer costs the stream 4 s in all -- not 4 s per word.
+struct Waiter {
+    volatile int *ok;
+    unsigned long long t0;
+    __device__ __forceinline__ bool alive() const { return *ok != 0; }
+    // one back-off step of a spin; false = give up
+    __device__ __forceinline__ bool pause() const
+    {
+        __nanosleep(200);
+        if (!*ok) return false;
+        if (now_ns() - t0 > kSpinLimitNs) { *ok = 0; return false; }
+        return true;
+    }
+};
+
+// Whole block: shared `ok` = 1 unless this rank's err word is already set (a broken exchange stays broken: later kernels
+// return at once instead of spinning again).
+__device__ __forceinline__ Waiter begin_wait(unsigned long long *local, const Layout &L, int *ok)
+{
+    if (threadIdx.x == 0) *ok = ld_volatile32(err_of(local, L)) == 0u ? 1 : 0;
+    __syncthreads();
+    return Waiter{ok, now_ns()};
+}
+__device__ __forceinline__ void raise_err(unsigned long long *local, const Layout &L, uint32_t *err_host, uint32_t code)
+{
+    atomicCAS(err_of(local, L), 0u, code);
+    if (err_host && *reinterpret_cast<volatile uint32_t *>(err_host) == 0u) *reinterpret_cast<volatile uint32_t *>(err_host) = code;
+}
 
 // Whole block.  Store this rank's block of `step` (n_words words at src, zero beyond, slot_words in all) into row `rank`
-// of ring slot step % depth of EVERY rank's table, each word with its sequence number; warp v serves ranks v, v+nwarps...
-__device__ void publish_block(const Peers &peers, const Layout &L, int rank, uint32_t step, const uint32_t *src, int n_words,
-                              uint32_t *local_copy, int *ok)
+// of ring slot `slot` of EVERY rank's table, each word with its sequence number; warp v serves ranks v, v+nwarps...
+__device__ void publish_block(const Peers &peers, const Layout &L, int rank, unsigned long long step, int slot, const uint32_t *src,
+                              int n_words, uint32_t *local_copy, uint32_t *err_host, int *ok)
 {
     unsigned long long *local = peers.p[rank];
-    const int slot = (int)(step % (uint32_t)L.depth);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    if (threadIdx.x == 0) *ok = 1;
-    __syncthreads();
+    const Waiter wt = begin_wait(local, L, ok);
     // flow control: every rank must have retired the step that last used this ring slot (local reads; free in steady state)
-    if (step >= (uint32_t)L.depth && lane == 0) {
-        const uint32_t want = step - (uint32_t)L.depth + 1u;
+    if (step >= (unsigned long long)L.depth && lane == 0 && wt.alive()) {
+        const uint32_t want = (uint32_t)(step - (unsigned long long)L.depth + 1ull);
         for (int r = warp; r < L.world; r += nwarps) {
             const uint32_t *a = ack_of(local, L) + r;
-            if ((int32_t)(ld_volatile32(a) - want) >= 0) continue;
-            const unsigned long long t0 = now_ns();
-            while ((int32_t)(ld_volatile32(a) - want) < 0) {
-                __nanosleep(200);
-                if (now_ns() - t0 > kSpinLimitNs) { *ok = 0; break; }
-            }
+            while ((int32_t)(ld_volatile32(a) - want) < 0)
+                if (!wt.pause()) break;
+            if (!wt.alive()) break;
         }
     }
     __syncthreads();
     if (!*ok) {
-        if (threadIdx.x == 0) atomicExch(err_of(local, L), 1u);
+        if (threadIdx.x == 0) raise_err(local, L, err_host, 1u);
         return;
     }
     const size_t row = ((size_t)slot * L.world + rank) * L.slot_words;
-    const unsigned long long seq = (unsigned long long)(step + 1u) << 32;
+    const unsigned long long seq = (unsigned long long)seq_of(step) << 32;
     for (int r = warp; r < L.world; r += nwarps) {
         unsigned long long *dst = peers.p[r] + row;
         for (int i = lane; i < L.slot_words; i += 32) st_volatile64(dst + i, seq | (i < n_words ? src[i] : 0u));
@@ -140,49 +177,64 @@ __device__ void publish_block(const Peers &peers, const Layout &L, int rank, uin
     }
 }
 
-// Whole block.  Wait until every word of ring slot step % depth carries step+1, copy the values to `out` (world x slot_words
-// u32, may be NULL), then retire the step at every rank.
-__device__ void collect_block(const Peers &peers, const Layout &L, int rank, uint32_t step, uint32_t *out, int *ok)
+// Whole block.  Wait until every word of ring slot `slot` carries the sequence number of `step`, copy the values to `out`
+// (world x slot_words u32, may be NULL), then retire the step at every rank.
+__device__ void collect_block(const Peers &peers, const Layout &L, int rank, unsigned long long step, int slot, uint32_t *out,
+                              uint32_t *err_host, int *ok)
 {
     unsigned long long *local = peers.p[rank];
-    const int slot = (int)(step % (uint32_t)L.depth);
-    if (threadIdx.x == 0) *ok = 1;
-    __syncthreads();
+    const Waiter wt = begin_wait(local, L, ok);
     const size_t n = (size_t)L.world * L.slot_words;
     const unsigned long long *src = local + (size_t)slot * n;
-    const uint32_t want = step + 1u;
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t want = seq_of(step);
+    for (size_t i = threadIdx.x; i < n && wt.alive(); i += blockDim.x) {
         unsigned long long v = ld_volatile64(src + i);
-        if ((uint32_t)(v >> 32) != want) {
-            const unsigned long long t0 = now_ns();
-            do {
-                __nanosleep(200);
-                v = ld_volatile64(src + i);
-                if (now_ns() - t0 > kSpinLimitNs) { *ok = 0; break; }
-            } while ((uint32_t)(v >> 32) != want);
+        while ((uint32_t)(v >> 32) != want) {
+            if (!wt.pause()) break;
+            v = ld_volatile64(src + i);
         }
         if (out) out[i] = (uint32_t)v;
     }
     __syncthreads();
     if (!*ok) {
-        if (threadIdx.x == 0) atomicExch(err_of(local, L), 2u);
+        if (threadIdx.x == 0) raise_err(local, L, err_host, 2u);
         return;
     }
     // retire: the slot may be overwritten once every rank has said so (all loads above have returned)
-    for (int r = threadIdx.x; r < L.world; r += blockDim.x) st_volatile32(ack_of(peers.p[r], L) + rank, want);
+    const uint32_t done = (uint32_t)(step + 1ull);
+    for (int r = threadIdx.x; r < L.world; r += blockDim.x) st_volatile32(ack_of(peers.p[r], L) + rank, done);
 }
 
-__global__ void __launch_bounds__(256) k_publish(Peers peers, Layout L, int rank, uint32_t step, const uint32_t *src, int n_words,
-                                                 uint32_t *local_copy)
+__global__ void __launch_bounds__(256) k_publish(Peers peers, Layout L, int rank, unsigned long long step, int slot,
+                                                 const uint32_t *src, int n_words, uint32_t *local_copy, uint32_t *err_host)
 {
     __shared__ int ok;
-    publish_block(peers, L, rank, step, src, n_words, local_copy, &ok);
+    publish_block(peers, L, rank, step, slot, src, n_words, local_copy, err_host, &ok);
 }
 
-__global__ void __launch_bounds__(256) k_collect(Peers peers, Layout L, int rank, uint32_t step, uint32_t *out)
+__global__ void __launch_bounds__(256) k_collect(Peers peers, Layout L, int rank, unsigned long long step, int slot, uint32_t *out,
+                                                 uint32_t *err_host)
 {
     __shared__ int ok;
-    collect_block(peers, L, rank, step, out, &ok);
+    collect_block(peers, L, rank, step, slot, out, err_host, &ok);
+}
+
+// Device-side rendezvous of all ranks IN the caller's stream: lane r tells rank r "I have reached gate number `count`",
+// then waits until rank r has said the same here.  Everything enqueued behind it starts within a few microseconds of
+// the same instant on every GPU (the hosts may be milliseconds apart).
+__global__ void __launch_bounds__(32) k_gate(Peers peers, Layout L, int rank, uint32_t count, uint32_t *err_host)
+{
+    __shared__ int ok;
+    unsigned long long *local = peers.p[rank];
+    const Waiter wt = begin_wait(local, L, &ok);
+    for (int r = threadIdx.x; r < L.world; r += 32) st_volatile32(gate_of(peers.p[r], L) + rank, count);
+    for (int r = threadIdx.x; r < L.world && wt.alive(); r += 32) {
+        const uint32_t *g = gate_of(local, L) + r;
+        while ((int32_t)(ld_volatile32(g) - count) < 0)
+            if (!wt.pause()) break;
+    }
+    __syncthreads();
+    if (!ok && threadIdx.x == 0) raise_err(local, L, err_host, 3u);
 }
 
 }  // namespace
@@ -204,6 +256,8 @@ struct lv_exchange {
     uint64_t steps = 0;                    // next step of lv_exchange_step
     bool stepping = false;
     int lag = 0;                           // step k's table is collected when step k+lag is issued (or on result)
+    uint32_t *h_err = nullptr;             // host-mapped mirror of the err word (read by the host without a copy)
+    uint32_t gates = 0;                    // lv_exchange_gate calls so far
 };
 
 namespace {
@@ -253,10 +307,13 @@ int lv_exchange_create(int device, int rank, int world, int depth, int slot_word
     const size_t bytes = x->L.bytes();
     cudaError_t e = cudaMalloc(&x->local, bytes);
     if (e == cudaSuccess) e = cudaMemset(x->local, 0, bytes);       // sequence number 0 = "nothing has arrived"
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&x->h_err), sizeof(uint32_t), cudaHostAllocMapped);
+    if (e == cudaSuccess) *x->h_err = 0u;
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         int rc = x_fail(e, "exchange buffer");
         cudaFree(x->local);
+        if (x->h_err) cudaFreeHost(x->h_err);
         delete x;
         return rc;
     }
@@ -284,6 +341,7 @@ void lv_exchange_destroy(lv_exchange *x)
     cudaFree(x->tables);
     cudaFree(x->own);
     cudaFree(x->local);
+    if (x->h_err) cudaFreeHost(x->h_err);
     delete x;
 }
 
@@ -341,7 +399,8 @@ int lv_exchange_publish(lv_exchange *x, uint64_t step, const uint32_t *d_block, 
     if (!x || n_words < 0 || n_words > x->L.slot_words || (n_words > 0 && !d_block)) return LV_E_ARG;
     if (!x->connected || x->stepping || step != x->published) return LV_E_STATE;      // steps are published in order, once
     DevGuard g(x->device);
-    k_publish<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, (uint32_t)step, d_block, n_words, nullptr);
+    k_publish<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, step, (int)(step % (uint64_t)x->L.depth), d_block,
+                                                        n_words, nullptr, x->h_err);
     X_CUDA(cudaGetLastError());
     x->published++;
     return LV_OK;
@@ -354,20 +413,44 @@ int lv_exchange_collect(lv_exchange *x, uint64_t step, uint32_t *d_table, void *
     // steps are collected in order, once, and only after this rank has published its own block of that step
     if (!x->connected || x->stepping || step != x->collected || step >= x->published) return LV_E_STATE;
     DevGuard g(x->device);
-    k_collect<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, (uint32_t)step, d_table);
+    k_collect<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, step, (int)(step % (uint64_t)x->L.depth), d_table,
+                                                        x->h_err);
     X_CUDA(cudaGetLastError());
     x->collected++;
     return LV_OK;
 }
 
-/* 0 = fine, 1 = a publish gave up waiting for a peer's ack, 2 = a collect gave up waiting for a peer's block */
+/* 0 = fine, 1 = a publish gave up waiting for a peer's ack, 2 = a collect gave up waiting for a peer's block, 3 = a gate
+ * gave up.  Reads the host-mapped mirror of the err word: no copy, no synchronisation (kernels that have finished have
+ * made their write visible). */
 int lv_exchange_error(lv_exchange *x)
 {
     if (!x) return LV_E_ARG;
+    return (int)*reinterpret_cast<volatile uint32_t *>(x->h_err);
+}
+
+/* Device-side rendezvous in `cuda_stream`: work enqueued behind it starts on every rank within microseconds of the same
+ * instant, however far apart the host threads are.  Collective: every rank calls it the same number of times. */
+int lv_exchange_gate(lv_exchange *x, void *cuda_stream)
+{
+    if (!x) return LV_E_ARG;
+    if (!x->connected) return LV_E_STATE;
     DevGuard g(x->device);
-    uint32_t v = 0;
-    X_CUDA(cudaMemcpy(&v, reinterpret_cast<uint32_t *>(x->local) + x->L.err_off32(), sizeof v, cudaMemcpyDeviceToHost));
-    return (int)v;
+    x->gates++;
+    k_gate<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, x->gates, x->h_err);
+    X_CUDA(cudaGetLastError());
+    return LV_OK;
+}
+
+/* Makes `cuda_stream` wait until the caller's d_summary of `step` (an lv_exchange_step) has been written: with the peer
+ * exchange that buffer is filled by the push kernel on the exchange's own stream, not by the fused kernel. */
+int lv_exchange_wait_summary(lv_exchange *x, uint64_t step, void *cuda_stream)
+{
+    if (!x) return LV_E_ARG;
+    if (!x->stepping || step >= x->steps || x->steps - step > (uint64_t)x->L.depth) return LV_E_STATE;
+    DevGuard g(x->device);
+    X_CUDA(cudaStreamWaitEvent((cudaStream_t)cuda_stream, x->ev_pushed[step % (uint64_t)x->L.depth], 0));
+    return LV_OK;
 }
 
 /* ---- the whole sharded step in one call -------------------------------------------------------------------------- */
@@ -395,8 +478,9 @@ int collect_through(lv_exchange *x, uint64_t step)
 {
     while (x->collected <= step) {
         const uint64_t j = x->collected;
-        k_collect<<<1, 256, 0, x->side>>>(x->peers, x->L, x->rank, (uint32_t)j,
-                                          x->tables + (size_t)(j % (uint64_t)x->L.depth) * x->world * x->L.slot_words);
+        const int slot = (int)(j % (uint64_t)x->L.depth);
+        k_collect<<<1, 256, 0, x->side>>>(x->peers, x->L, x->rank, j, slot, x->tables + (size_t)slot * x->world * x->L.slot_words,
+                                          x->h_err);
         X_CUDA(cudaGetLastError());
         x->collected = j + 1;
     }
@@ -437,7 +521,7 @@ int lv_exchange_step(lv_exchange *x, lv_ctx *ctx, const uint8_t *d_i420, int fir
     }
     X_CUDA(cudaEventRecord(x->ev_kernel[slot], st));
     X_CUDA(cudaStreamWaitEvent(x->side, x->ev_kernel[slot], 0));
-    k_publish<<<1, 256, 0, x->side>>>(x->peers, x->L, x->rank, (uint32_t)k, block, (int)n_words, d_summary);
+    k_publish<<<1, 256, 0, x->side>>>(x->peers, x->L, x->rank, k, slot, block, (int)n_words, d_summary, x->h_err);
     X_CUDA(cudaGetLastError());
     X_CUDA(cudaEventRecord(x->ev_pushed[slot], x->side));
     x->published = k + 1;
@@ -467,7 +551,8 @@ int lv_exchange_result(lv_exchange *x, uint64_t step, const uint32_t **d_table)
     X_CUDA(cudaStreamSynchronize(x->side));
     const int err = lv_exchange_error(x);
     if (err != 0) {
-        snprintf(x_err, sizeof x_err, "peer exchange gave up waiting for a peer (%s)", err == 1 ? "publish" : "collect");
+        snprintf(x_err, sizeof x_err, "peer exchange gave up waiting for a peer (%s)",
+                 err == 1 ? "publish" : err == 2 ? "collect" : "gate");
         return LV_E_STATE;
     }
     *d_table = x->tables + (size_t)(step % (uint64_t)x->L.depth) * x->world * x->L.slot_words;

@@ -348,7 +348,9 @@ int launch_format(int kind, int w, int h, const uint8_t *in, uint8_t *out, int n
         const int nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
         const uint8_t *i0 = in + (size_t)f0 * inb;
         uint8_t *o0 = out + (size_t)f0 * outb;
-        if (w % 32 == 0 && h % 4 == 0) {
+        // the vector kernels move 16-byte words: both buffers must be 16-byte aligned, otherwise the byte kernels run
+        const bool al16 = ((reinterpret_cast<uintptr_t>(i0) | reinterpret_cast<uintptr_t>(o0)) & 15) == 0;
+        if (w % 32 == 0 && h % 4 == 0 && al16 && inb % 16 == 0 && outb % 16 == 0) {
             // vector kernels: one work item = 16 px x 2 rows (kinds 1, 3, 5) or 32 px x 4 rows (kinds 2, 4)
             const size_t items = (kind == 2 || kind == 4) ? (size_t)(w / 32) * (h / 4) : (size_t)(w / 16) * (h / 2);
             unsigned vx = (unsigned)((items + 255) / 256);

@@ -50,6 +50,10 @@ struct KArgs {
     uint16_t *mb_count;
     uint8_t *mb_map;
     uint32_t *summary;
+    // kBox instantiation only: per-frame object windows {x0,x1,y0,y1} (inclusive) and boxes {min_x,max_x,min_y,max_y}
+    const int4 *windows;
+    int4 *boxes;
+    int n_obj;
 };
 
 // Cache policies (A/B measured on B200, profiles/README.md).  Loads: 0 = read-only path (ld.global.nc), 1 = .cs
@@ -137,8 +141,12 @@ __device__ __forceinline__ void convert_row16(const uint4 &y, const Chroma2 (&c)
 
 // All addressing is a block-uniform 64-bit base (frame / plane starts) plus one 32-bit per-thread offset;
 // the frame -> (stream, t) split is a multiply-high by a host-computed reciprocal.  The optional mask
-// outputs live in their own instantiation (kMask) so the common path carries none of their code.
-template <bool kConv, bool kDiff, bool kMask>
+// outputs live in their own instantiation (kMask) so the common path carries none of their code; so does the object
+// box of the step after the path (kBox: lib/JM/image.c:4818-4838 -- min / max x, y of the changed pixels inside each
+// object's window, accumulated here so that no mask ever goes through HBM).
+constexpr int kMaxObjects = 16;
+
+template <bool kConv, bool kDiff, bool kMask, bool kBox = false>
 __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
 {
     const Geom &g = a.g;
@@ -161,6 +169,7 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
     const int w = g.w;
 
     uint32_t cnt = 0;
+    [[maybe_unused]] uint32_t bm0 = 0, bm1 = 0;      // kBox: the thread's two 16-pixel mask rows
     if (active) {
         const uint8_t *yf = a.y0 + (size_t)f * a.y_stride;
         const uint32_t off = (uint32_t)row0 * (uint32_t)w + (uint32_t)unit * 16u;
@@ -177,9 +186,10 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
             const uint4 p1 = ld16_stream(ref + off + w);
             const uint32_t tol4 = (uint32_t)a.tol * 0x01010101u;
             const uint32_t ntol7 = ~tol4 & 0x7f7f7f7fu;
-            if constexpr (kMask) {
+            if constexpr (kMask || kBox) {
                 const uint32_t m0 = diff_mask16(y0, p0, tol4, ntol7);
                 const uint32_t m1 = diff_mask16(y1, p1, tol4, ntol7);
+                if constexpr (kBox) { bm0 = m0; bm1 = m1; }
                 cnt = (uint32_t)(__popc(m0) + __popc(m1)) << 7;
                 if (a.mask_bits) {
                     uint16_t *mb = a.mask_bits + ((size_t)f * g.h + row0) * g.units + unit;
@@ -223,6 +233,54 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
         }
     }
 
+    if constexpr (kBox) {
+        // Per object: clip the thread's mask rows to the window, reduce min / max over the warp (REDUX), park the warp's
+        // result; the first warp finishes the block behind the barrier below.  A block whose rectangle misses the window
+        // (block-uniform test) skips the object.
+        __shared__ int sbox[kMaxObjects][8][4];
+        const int xs = unit * 16;
+        for (int k = 0; k < a.n_obj; k++) {
+            const int4 wd = __ldg(a.windows + (size_t)f * a.n_obj + k);      // x0, x1, y0, y1
+            int lo = wd.x - xs, hi = wd.y - xs;
+            lo = lo < 0 ? 0 : lo;
+            hi = hi > 15 ? 15 : hi;
+            const uint32_t cm = (active && lo <= hi) ? ((2u << hi) - (1u << lo)) : 0u;
+            const uint32_t r0 = (row0 >= wd.z && row0 <= wd.w) ? bm0 & cm : 0u;
+            const uint32_t r1 = (row0 + 1 >= wd.z && row0 + 1 <= wd.w) ? bm1 & cm : 0u;
+            const uint32_t any = r0 | r1;
+            int mnx = 0x7fffffff, mxx = -0x7fffffff, mny = 0x7fffffff, mxy = -0x7fffffff;
+            if (any) {
+                mnx = xs + __ffs((int)any) - 1;
+                mxx = xs + 31 - __clz((int)any);
+                mny = r0 ? row0 : row0 + 1;
+                mxy = r1 ? row0 + 1 : row0;
+            }
+            mnx = __reduce_min_sync(0xffffffffu, mnx);
+            mxx = __reduce_max_sync(0xffffffffu, mxx);
+            mny = __reduce_min_sync(0xffffffffu, mny);
+            mxy = __reduce_max_sync(0xffffffffu, mxy);
+            if (tx == 0) {
+                sbox[k][ty][0] = mnx; sbox[k][ty][1] = mxx; sbox[k][ty][2] = mny; sbox[k][ty][3] = mxy;
+            }
+        }
+        __syncthreads();
+        if (ty == 0) {
+            for (int j = tx; j < 4 * a.n_obj; j += 32) {
+                const int k = j >> 2, c = j & 3;
+                int v = sbox[k][0][c];
+#pragma unroll
+                for (int i = 1; i < 8; i++) v = (c & 1) ? max(v, sbox[k][i][c]) : min(v, sbox[k][i][c]);
+                int *dst = reinterpret_cast<int *>(a.boxes + (size_t)f * a.n_obj + k) + c;
+                // a changed pixel was seen (v is not the neutral value) and it improves what is there: one atomic
+                if (c & 1) {
+                    if (v != -0x7fffffff && v > *reinterpret_cast<volatile int *>(dst)) atomicMax(dst, v);
+                } else {
+                    if (v != 0x7fffffff && v < *reinterpret_cast<volatile int *>(dst)) atomicMin(dst, v);
+                }
+            }
+        }
+    }
+
     if constexpr (kDiff) {
         // 8 row-pair partial counts per macroblock -> shared memory -> the first warp finishes the block
         __shared__ uint32_t part[8][32];
@@ -256,7 +314,7 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
     }
 }
 
-template <bool kConv, bool kDiff, bool kMask>
+template <bool kConv, bool kDiff, bool kMask, bool kBox = false>
 int launch_tile_t(const KArgs &a, int total_frames, cudaStream_t st)
 {
     int launches = 0;
@@ -274,12 +332,24 @@ int launch_tile_t(const KArgs &a, int total_frames, cudaStream_t st)
             b.mbw_magic = (uint32_t)(((1ULL << 32) + mbw - 1) / mbw);
             grid = dim3((unsigned)((mbs + 31) / 32), 1, nf);
         }
-        k_tile<kConv, kDiff, kMask><<<grid, block, 0, st>>>(b);
+        k_tile<kConv, kDiff, kMask, kBox><<<grid, block, 0, st>>>(b);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return -(int)e;
         launches++;
     }
     return launches;
+}
+
+// One launch in front of a step with boxes: zero the summary (in place of the memset) and set every box to the reference's
+// initial values {x1+1, x0-1, y1+1, y0-1} (lib/JM/image.c:4818-4821), which are also the result for an empty window.
+__global__ void k_step_init(uint32_t *summary, int n_summary_words, const int4 *windows, int4 *boxes, int n_boxes)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (summary && i < n_summary_words) summary[i] = 0u;
+    if (i < n_boxes) {
+        const int4 w = windows[i];
+        boxes[i] = make_int4(w.y + 1, w.x - 1, w.w + 1, w.z - 1);
+    }
 }
 
 template <bool kConv, bool kDiff>
@@ -289,6 +359,7 @@ int launch_tile(KArgs a, int total_frames, cudaStream_t st)
     // the multiply-high division is exact for f < 2^16 and n_frames < 2^16; longer batches are cut by the caller
     a.nf_magic = a.n_frames > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)a.n_frames - 1) / (uint64_t)a.n_frames) : 0u;
     const bool mask = a.mask_bits || a.mask_bytes;
+    if (kDiff && a.boxes) return launch_tile_t<kConv, kDiff, kDiff, kDiff>(a, total_frames, st);   // masks too, when asked
     if (kDiff && mask) return launch_tile_t<kConv, kDiff, kDiff>(a, total_frames, st);
     return launch_tile_t<kConv, kDiff, false>(a, total_frames, st);
 }
@@ -352,9 +423,9 @@ static bool use_strip() { return kernel_variant() == 2; }
 
 int launch_step(const StepArgs &s, cudaStream_t st)
 {
-    if (use_strip() && !s.static_ref)
+    if (use_strip() && !s.static_ref && !s.boxes)
         if (int r = launch_step_strip(s, st)) return r;
-    if (use_tma() && !s.static_ref)
+    if (use_tma() && !s.static_ref && !s.boxes)
         if (int r = launch_step_tma(s, st)) return r;   // 0 = geometry/alignment not eligible for the TMA pipeline
     KArgs a{};
     a.static_ref = s.static_ref;
@@ -363,6 +434,8 @@ int launch_step(const StepArgs &s, cudaStream_t st)
     a.tol = s.tol; a.mb_thresh = s.mb_thresh;
     a.bgr = s.bgr; a.mask_bits = s.mask_bits; a.mask_bytes = s.mask_bytes;
     a.mb_count = s.mb_count; a.mb_map = s.mb_map; a.summary = s.summary;
+    a.windows = reinterpret_cast<const int4 *>(s.windows); a.boxes = reinterpret_cast<int4 *>(s.boxes); a.n_obj = s.n_obj;
+    if (s.boxes && (s.n_obj < 1 || s.n_obj > kMaxObjects || !s.windows)) return -(int)cudaErrorInvalidValue;
     if (s.n_frames > 65535) return -(int)cudaErrorInvalidValue;
     // the kernel's frame -> (stream, t) split is exact below 2^16 frames per launch group: cut by streams
     const int group = 65535 / s.n_frames;
@@ -381,11 +454,23 @@ int launch_step(const StepArgs &s, cudaStream_t st)
         if (a.mb_count) b.mb_count = a.mb_count + f0 * mbs;
         if (a.mb_map) b.mb_map = a.mb_map + f0 * mbs;
         if (a.summary) b.summary = a.summary + 2 * f0;
+        if (a.boxes) { b.windows = a.windows + f0 * s.n_obj; b.boxes = a.boxes + f0 * s.n_obj; }
         const int r = s.bgr ? launch_tile<true, true>(b, ns * s.n_frames, st) : launch_tile<false, true>(b, ns * s.n_frames, st);
         if (r < 0) return r;
         launches += r;
     }
     return launches;
+}
+
+int launch_step_init(uint32_t *summary, size_t n_frames, const int *windows, int *boxes, int n_obj, cudaStream_t st)
+{
+    const size_t nb = n_frames * (size_t)n_obj, ns = summary ? 2 * n_frames : 0, n = nb > ns ? nb : ns;
+    if (n == 0) return 0;
+    if (n > 0x7fffffffu) return -(int)cudaErrorInvalidValue;
+    k_step_init<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(summary, (int)ns, reinterpret_cast<const int4 *>(windows),
+                                                            reinterpret_cast<int4 *>(boxes), (int)nb);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
 }
 
 int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st)

@@ -38,6 +38,10 @@ struct StepArgs {
     uint16_t *mb_count;
     uint8_t *mb_map;
     uint32_t *summary;        // 2 per frame; must be zeroed before the launch
+    // object boxes accumulated by the fused kernel (optional; boxes must be initialised: launch_step_init)
+    const int *windows;       // n_obj x {x0, x1, y0, y1} per frame, inclusive, 16-byte aligned
+    int *boxes;               // n_obj x {min_x, max_x, min_y, max_y} per frame, 16-byte aligned
+    int n_obj;                // 1 .. 16
 };
 
 // difference of explicit (cur, ref) plane pairs: frame i of cur_y against frame i of ref_y
@@ -56,6 +60,7 @@ struct DiffArgs {
 // width % 16 == 0, height % 2 == 0.  Return the number of kernels launched (>0) or a negative
 // cudaError_t value (-(int)err).
 int launch_step(const StepArgs &a, cudaStream_t st);
+int launch_step_init(uint32_t *summary, size_t n_frames, const int *windows, int *boxes, int n_obj, cudaStream_t st);
 int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st);
 int launch_diff(const DiffArgs &a, cudaStream_t st);
 
@@ -82,6 +87,10 @@ int launch_narrow(const Geom &g, const uint16_t *pic16, int n_frames, int size_x
                   uint8_t *i420, cudaStream_t st);
 int launch_object_box(int w, int h, const uint8_t *mask, bool bits, int n_frames, int x0, int x1, int y0, int y1, int *d_boxes,
                       cudaStream_t st);
+
+// the object bookkeeping either side of the box (lib/JM/image.c:4786-4789 and 4840-4848); objects = {PosX, PosY, Width, Height}
+int launch_object_windows(int w, int h, const int *objects, int n, int hor_margin, int ver_margin, int *windows, cudaStream_t st);
+int launch_object_update(const int *boxes, int n, int *objects, cudaStream_t st);
 
 // lv_formats.cu: the other five cscc.lib converters (kind 1 RGB24->YV12, 2 YVU9->YV12, 3 YUY2->YV12, 4 YV12->YVU9,
 // 5 YV12->YUY2)

@@ -48,7 +48,10 @@ class PendingGather:
     def flush(self):
         """Nothing to do: the collective was started when the handle was made (same interface as PendingPeerGather)."""
 
-    def result(self):
+    def wait_summary(self, stream=None):
+        """Nothing to do: on this path out["summary"] is written in-stream by the fused kernel."""
+
+    def result(self, copy=True):
         import torch
         if self.work is not None:
             self.work.wait()
@@ -186,10 +189,10 @@ class PeerExchange:
         n, d = n_streams * n_frames, ctx.device
         k = self._C.c_uint64()
         self._capi.check(self._capi.lib().lv_exchange_step(
-            self._h, ctx._h, _dev_ptr(i420, torch.uint8, n * ctx.frame_bytes, "i420", d), first_stream, n_streams, n_frames,
-            _dev_ptr(out.get("bgr"), torch.uint8, n * ctx.bgr_bytes, "bgr", d),
+            self._h, ctx._h, _dev_ptr(i420, torch.uint8, n * ctx.frame_bytes, "i420", d, 16), first_stream, n_streams, n_frames,
+            _dev_ptr(out.get("bgr"), torch.uint8, n * ctx.bgr_bytes, "bgr", d, 16),
             _dev_ptr(out.get("mask_bits"), torch.int16, n * ctx.mask_units, "mask_bits", d),
-            _dev_ptr(out.get("mask_bytes"), torch.uint8, n * ctx.px, "mask_bytes", d),
+            _dev_ptr(out.get("mask_bytes"), torch.uint8, n * ctx.px, "mask_bytes", d, 16),
             _dev_ptr(out.get("mb_count"), torch.int16, n * ctx.mbs, "mb_count", d),
             _dev_ptr(out.get("mb_map"), torch.uint8, n * ctx.mbs, "mb_map", d),
             _dev_ptr(out.get("summary"), torch.int32, n * 2, "summary", d),
@@ -200,14 +203,25 @@ class PeerExchange:
         """Push the newest step's block now (it otherwise travels in front of the next step); asynchronous."""
         self._capi.check(self._capi.lib().lv_exchange_flush(self._h), "lv_exchange_flush")
 
-    def result(self, step):
-        """int32 CUDA tensor [world, slot_words]: the table of `step` (a copy; blocks until every block has arrived)."""
+    def gate(self, stream):
+        """lv_exchange_gate: device-side rendezvous of all ranks in `stream` (collective)."""
+        self._capi.check(self._capi.lib().lv_exchange_gate(self._h, stream.cuda_stream), "lv_exchange_gate")
+
+    def wait_summary(self, step, stream):
+        """lv_exchange_wait_summary: `stream` waits until the caller's d_summary of `step` has been written."""
+        self._capi.check(self._capi.lib().lv_exchange_wait_summary(self._h, step, stream.cuda_stream),
+                         "lv_exchange_wait_summary")
+
+    def result(self, step, copy=True):
+        """int32 CUDA tensor [world, slot_words]: the table of `step` (blocks until every block has arrived).
+        copy=False returns a view of the exchange's own ring slot, valid until `depth` further steps are issued."""
         from .api import _DevView
         p = self._C.c_void_p()
         self._capi.check(self._capi.lib().lv_exchange_result(self._h, step, self._C.byref(p)), "lv_exchange_result")
         nbytes = 4 * self.world * self.slot_words
         import torch
-        return _DevView(p.value, nbytes, self.device).tensor().view(torch.int32).reshape(self.world, self.slot_words).clone()
+        t = _DevView(p.value, nbytes, self.device).tensor().view(torch.int32).reshape(self.world, self.slot_words)
+        return t.clone() if copy else t
 
 
 class PendingPeerGather:
@@ -222,11 +236,23 @@ class PendingPeerGather:
         every rank before asking any of them for the result)."""
         self.owner.exchange.flush()
 
-    def result(self):
+    def wait_summary(self, stream=None):
+        """Make `stream` (default: the current one) wait until out["summary"] of this step holds this rank's block: with
+        the peer exchange it is written by the push kernel on the exchange's own stream, not in-stream."""
         import torch
         o = self.owner
-        tab = o.exchange.result(self.step)
+        o.exchange.wait_summary(self.step, stream or torch.cuda.current_stream(o.device))
+
+    def result(self, copy=True):
+        """[total_streams, n_frames, 2].  copy=False: when every rank owns the same number of streams the table is
+        returned as a view of the exchange's ring slot (no kernel at all; valid for RING further steps)."""
+        import torch
+        o = self.owner
         cap = max_shard(o.total_streams, o.world)
+        even = cap * o.world == o.total_streams and cap * self.n_frames * 2 == o.exchange.slot_words
+        tab = o.exchange.result(self.step, copy=copy or not even)
+        if even:
+            return tab.reshape(o.total_streams, self.n_frames, 2)
         tab = tab[:, : cap * self.n_frames * 2].reshape(o.world, cap, self.n_frames, 2)
         parts = [tab[r, :shard_range(o.total_streams, o.world, r)[1]] for r in range(o.world)]
         return torch.cat(parts, dim=0)
@@ -327,10 +353,27 @@ class ShardedContext:
                                     n_frames, group=group)
         return None
 
+    def gate(self, group=None):
+        """Align the GPUs of all ranks: what is enqueued on the current stream after this call starts within microseconds
+        of the same instant on every rank, however far apart the host processes are.  Peer exchange: one tiny kernel
+        that signals and waits over NVLink (lv_exchange_gate); otherwise an all-reduce of one word on the stream."""
+        import torch
+        import torch.distributed as dist
+        if self.exchange is not None:
+            self.exchange.gate(torch.cuda.current_stream(self.device))
+        elif self.world > 1 and dist.is_available() and dist.is_initialized():
+            t = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", self.device))
+            dist.all_reduce(t, group=group)
+
     def step_async(self, i420_local, n_frames, out, group=None):
         """Fused kernel, then the summary all-gather started WITHOUT blocking the compute stream: the returned
         PendingGather completes while the next steps' kernels run.  At most RING gathers are in flight; the one
-        issued RING steps ago is waited for before its buffers are reused."""
+        issued RING steps ago is waited for before its buffers are reused.
+
+        NOTE on out["summary"]: with the library all-gather it is valid in-stream right behind the fused kernel (as in
+        step()).  With the peer exchange (exchange="p2p") the fused kernel accumulates into the exchange's own ring row
+        and out["summary"] is filled by the push kernel on the exchange's side stream: a consumer on the compute
+        stream must call handle.wait_summary() first (or use handle.result())."""
         import torch
         import torch.distributed as dist
         if self.exchange is None and self._want_p2p and self.world > 1:

@@ -391,6 +391,31 @@ void lvo_object_box(const uint8_t *mask, int width, int x0, int x1, int y0, int 
     box[0] = min_obj_x; box[1] = max_obj_x; box[2] = min_obj_y; box[3] = max_obj_y;
 }
 
+/* The object bookkeeping either side of the box in motion_segment's I-frame branch.
+ * image.h:23-24: #define ClipX(x) (x<0?0:(x>=iwidth?iwidth-1:x)), ClipY likewise with iheight. */
+static int clip_to(int x, int n) { return x < 0 ? 0 : (x >= n ? n - 1 : x); }
+
+void lvo_object_window(const int obj[4], int width, int height, int hor_margin, int ver_margin, int win[4])
+{
+    /* image.c:4786-4789; obj = {PosX, PosY, Width, Height}; win = {min_x, max_x, min_y, max_y} */
+    win[0] = clip_to(obj[0] - obj[2] / 2 - hor_margin, width);
+    win[1] = clip_to(obj[0] + obj[2] / 2 + hor_margin, width);
+    win[2] = clip_to(obj[1] - obj[3] / 2 - ver_margin, height);
+    win[3] = clip_to(obj[1] + obj[3] / 2 + ver_margin, height);
+}
+
+void lvo_object_update(const int box[4], int obj[4])
+{
+    /* image.c:4840-4848; box = {min_obj_x, max_obj_x, min_obj_y, max_obj_y} */
+    const int min_obj_x = box[0], max_obj_x = box[1], min_obj_y = box[2], max_obj_y = box[3];
+    if ((min_obj_x < max_obj_x) && (min_obj_y < max_obj_y)) {
+        obj[0] = (int)(min_obj_x + (max_obj_x - min_obj_x) / 2);
+        obj[1] = (int)(min_obj_y + (max_obj_y - min_obj_y) / 2);
+        obj[2] = (int)(max_obj_x - min_obj_x);
+        obj[3] = (int)(max_obj_y - min_obj_y);
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * Generators; all arithmetic uint32 wrap-around.
  * ---------------------------------------------------------------------------------------- */

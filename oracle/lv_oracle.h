@@ -92,6 +92,9 @@ void lvo_picture16_to_i420(const uint16_t *pic16, int size_x, int size_y, int cr
 /* box[4] = {min_x, max_x, min_y, max_y} over mask==1 inside the window [x0..x1]x[y0..y1] (inclusive);
  * empty => {x1+1, x0-1, y1+1, y0-1} exactly as the reference initialises them. */
 void lvo_object_box(const uint8_t *mask, int width, int x0, int x1, int y0, int y1, int box[4]);
+/* lib/JM/image.c:4786-4789 (window of an object, ClipX/ClipY of image.h:23-24) and 4840-4848 (object from its box) */
+void lvo_object_window(const int obj[4], int width, int height, int hor_margin, int ver_margin, int win[4]);
+void lvo_object_update(const int box[4], int obj[4]);
 
 /* ---- synthetic generators; counter based, identical in C / numpy / CUDA --- */
 uint32_t lvo_lowbias32(uint32_t x);

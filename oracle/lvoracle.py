@@ -151,6 +151,24 @@ def object_box(mask, w, x0, x1, y0, y1):
     return tuple(box)
 
 
+def object_window(obj, w, h, hor_margin=8, ver_margin=8):
+    """{min_x, max_x, min_y, max_y} of an object {PosX, PosY, Width, Height} (lib/JM/image.c:4786-4789)."""
+    L = lib()
+    L.lvo_object_window.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    o, win = (C.c_int * 4)(*[int(v) for v in obj]), (C.c_int * 4)()
+    L.lvo_object_window(o, w, h, hor_margin, ver_margin, win)
+    return tuple(win)
+
+
+def object_update(box, obj):
+    """Object {PosX, PosY, Width, Height} after the box (lib/JM/image.c:4840-4848)."""
+    L = lib()
+    L.lvo_object_update.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    b, o = (C.c_int * 4)(*[int(v) for v in box]), (C.c_int * 4)(*[int(v) for v in obj])
+    L.lvo_object_update(b, o)
+    return tuple(o)
+
+
 # converter name -> (oracle32 mode, input bytes per 8 px, output bytes per 8 px)
 FORMATS = {"rgb24_to_yv12": (1, 24, 12), "yvu9_to_yv12": (2, 9, 12), "yuy2_to_yv12": (3, 16, 12),
            "yv12_to_yvu9": (4, 12, 9), "yv12_to_yuy2": (5, 12, 16)}

@@ -82,7 +82,7 @@ def test_exchange_argument_checks_need_no_gpu(built, lv):
     """lv_exchange_*: sizes are pure arithmetic; creation without a device reports LV_E_NODEVICE (never a fallback)."""
     import ctypes as C
     L = lv.lib()
-    assert L.lv_exchange_bytes(8, 8, 128) == 8 * (8 * 8 * 128) + 4 * 8 + 16     # u64 words + acks + err, 16-byte multiple
+    assert L.lv_exchange_bytes(8, 8, 128) == 8 * (8 * 8 * 128) + 4 * 8 + 4 * 8 + 16     # u64 words + acks + gates + err, 16-byte multiple
     assert L.lv_exchange_bytes(0, 8, 128) == 0 and L.lv_exchange_bytes(8, 1, 128) == 0
     h = C.c_void_p()
     assert L.lv_exchange_create(0, 2, 2, 8, 16, C.byref(h)) == -1          # rank out of range: LV_E_ARG

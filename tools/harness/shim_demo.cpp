@@ -29,5 +29,18 @@ int main(int argc, char **argv)
     prev[0] = 0;                                        // one pixel differs by 128 > tol
     FrameDiff_MB(srcY.data(), prev.data(), width, height, 20, 0, mask.data(), cnt.data(), map.data());
     printf("changed pixels in macroblock 0: %d, block map: %d\n", cnt[0], map[0]);
-    return 0;
+
+    // CMainDlg::DisplayPic (MainDlg.cpp:937-977): five pictures, the dialog's own pointer arrays, one pipelined call
+    unsigned char *srcYs[5], *srcUs[5], *srcVs[5], *RGBbufs[5];
+    std::vector<std::vector<unsigned char>> own;
+    for (int i = 0; i < 5; i++) {
+        own.emplace_back(YSize, (unsigned char)(16 + 40 * i)); srcYs[i] = own.back().data();
+        own.emplace_back(UVSize, 128); srcUs[i] = own.back().data();
+        own.emplace_back(UVSize, 128); srcVs[i] = own.back().data();
+        own.emplace_back(3 * YSize); RGBbufs[i] = own.back().data();
+    }
+    const int rc = pCon.YV12_to_RGB24(srcYs, srcUs, srcVs, RGBbufs, 5, width, height);
+    printf("five pictures in one call: rc %d, first blue bytes %d %d %d %d %d (expect 0 46 93 139 186)\n", rc, RGBbufs[0][0],
+           RGBbufs[1][0], RGBbufs[2][0], RGBbufs[3][0], RGBbufs[4][0]);
+    return rc;
 }
