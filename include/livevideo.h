@@ -145,8 +145,8 @@ LV_API int lv_reset_prev_luma(lv_ctx *ctx, void *cuda_stream);   /* back to all 
  * Alignment (checked, LV_E_ARG otherwise -- the kernels move 16-byte words, and a misaligned vector access would be a
  * sticky CUDA error): d_i420, d_bgr, d_mask_bytes 16 bytes; d_mask_bits, d_mb_count 2 bytes; d_summary 4 bytes.  The same
  * holds for lv_convert_batch (d_i420, d_bgr) and lv_diff_batch (d_cur_y, d_ref_y, d_mask_bytes 16 bytes).
- * lv_write_bks, lv_narrow_pictures and lv_convert_format accept any byte alignment (they fall back to narrower
- * accesses).  Anything from cudaMalloc / a torch allocation is 256-byte aligned; only sub-buffers at odd offsets are
+ * lv_write_bks needs 4-byte aligned frames (16-byte aligned ones take the vector kernel); lv_narrow_pictures (beyond the
+ * 2 bytes of its uint16 input) and lv_convert_format accept any byte alignment (they fall back to byte accesses).  Anything from cudaMalloc / a torch allocation is 256-byte aligned; only sub-buffers at odd offsets are
  * affected.
  * Streams keep their state independently: stepping streams [first_stream, first_stream + n_streams) neither reads nor
  * copies the state of any other stream. */

@@ -62,6 +62,21 @@ class ColorSpaceConversions:
                                                     arr(dst_ori, 3 * px, "dst_ori", True), n, width, height),
                    "lv_convert_host_multi")
 
+    def bind_multi(self, src0, src1, src2, dst_ori, width, height):
+        """The same call with the pointer arrays built ONCE (the dialog's srcY[5] ... RGBbuf[5] are members that never
+        change, MainDlg.h): returns a function that issues lv_convert_host_multi on them."""
+        n = len(src0)
+        px = width * height
+        arrs = [(C.c_void_p * n)(*[_host_ptr(a, np.uint8, nb, name, wr) for a in xs])
+                for xs, nb, name, wr in ((src0, px, "src0", False), (src1, px // 4, "src1", False),
+                                         (src2, px // 4, "src2", False), (dst_ori, 3 * px, "dst_ori", True))]
+        keep = (list(src0), list(src1), list(src2), list(dst_ori))      # the arrays must outlive the binding
+        fn = capi.lib().lv_convert_host_multi
+
+        def call(_keep=keep):
+            capi.check(fn(arrs[0], arrs[1], arrs[2], arrs[3], n, width, height), "lv_convert_host_multi")
+        return call
+
     # the five methods the application never calls (Convert.h:25-30): same (in, out, w, h) convention, in place
     def _fmt(self, name, kind, inp, out, w, h):
         if w <= 0 or h <= 0:

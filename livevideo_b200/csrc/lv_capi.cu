@@ -438,7 +438,9 @@ int lv_write_bks(lv_ctx *c, const uint8_t *d_cur, const uint8_t *d_bkd, int n_fr
 {
     if (!c || !d_cur || !d_bkd || !d_out || n_frames < 0 || tol < 0 || tol > 255) return LV_E_ARG;
     if (d_obj_bits && c->g.w % 16 != 0) return LV_E_SIZE;
-    if (!aligned(d_obj_bits, 2)) return misaligned("d_obj_bits (2 bytes)");   // the frames themselves may sit anywhere
+    // 16-byte aligned frames take the vector kernel, anything 4-byte aligned the word kernel
+    if (!aligned(d_cur, 4) || !aligned(d_bkd, 4) || !aligned(d_out, 4)) return misaligned("d_cur_i420 / d_bkd_i420 / d_out_i420 (4 bytes)");
+    if (!aligned(d_obj_bits, 2)) return misaligned("d_obj_bits (2 bytes)");
     if (n_frames == 0) return LV_OK;
     DeviceGuard guard(c->device);
     return launch_result(lv::launch_write_bks(c->g, d_cur, d_bkd, n_frames, tol, d_out, d_obj_bits, (cudaStream_t)cuda_stream),

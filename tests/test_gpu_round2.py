@@ -249,7 +249,7 @@ def test_host_step_256_streams_cut_by_streams(lv, orc, torch_cuda):
 # ---- errors are codes ---------------------------------------------------------------------------------------------------
 def test_misaligned_device_pointers_are_refused_not_fatal(lv, orc, torch_cuda):
     """A sub-buffer at an odd offset must give LV_E_ARG (-1), not a sticky cudaErrorMisalignedAddress; afterwards the
-    context still works.  lv_write_bks / lv_convert_format accept any alignment and stay bit-exact."""
+    context still works.  lv_write_bks (4-byte) / lv_convert_format (any alignment) stay bit-exact off the 16-byte grid."""
     torch = torch_cuda
     w, h = 64, 48
     ctx = lv.Context(w, h, 1, 20, 0)
@@ -280,15 +280,17 @@ def test_misaligned_device_pointers_are_refused_not_fatal(lv, orc, torch_cuda):
     ctx.convert_diff_batch(torch.from_numpy(fr.reshape(-1)).cuda(), 1, 1, out)
     torch.cuda.synchronize()
     assert np.array_equal(out["bgr"].cpu().numpy(), ref["bgr"])
-    # entries that take any alignment: frames at odd offsets
+    # entries that take narrower alignment: frames off the 16-byte grid
     cur = orc.gen_batch("camera", 2, 1, 2, w, h).reshape(-1)
-    for off in (0, 1, 3):
-        d_cur = big[off:off + 2 * fb]
+    assert L.lv_write_bks(ctx._h, C.c_void_p(big.data_ptr() + 1), p(big), 1, 25, C.c_void_p(bgr_big.data_ptr()), None, st) == -1
+    for off in (0, 4, 3):
+        boff = off & ~3                                   # lv_write_bks: 4-byte grid
+        d_cur = big[boff:boff + 2 * fb]
         d_cur.copy_(torch.from_numpy(cur))
         d_bkd = torch.from_numpy(cur[:fb].copy()).cuda()
         d_o = torch.zeros(2 * fb + 16, dtype=torch.uint8, device="cuda")
-        ctx.write_bks(d_cur, d_bkd, 2, d_o[off:off + 2 * fb], tol=25)
-        got = d_o[off:off + 2 * fb].cpu().numpy()
+        ctx.write_bks(d_cur, d_bkd, 2, d_o[boff:boff + 2 * fb], tol=25)
+        got = d_o[boff:boff + 2 * fb].cpu().numpy()
         want = np.concatenate([orc.write_bks(cur[i * fb:(i + 1) * fb], cur[:fb], w, h, 25) for i in range(2)])
         assert np.array_equal(got, want), off
         src = torch.zeros(3 * w * h + 16, dtype=torch.uint8, device="cuda")
