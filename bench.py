@@ -289,16 +289,22 @@ def timed_steps(torch, D, sc, d_in, nf, out, steps, warmup, sampler=None, exchan
     ev0.record()
     for _ in range(steps):
         pending = one()
+    tail_ms = 0.0
     if pending is not None:
+        ev_last = torch.cuda.Event(enable_timing=True)
+        ev_last.record()                             # behind the last fused kernel: what follows is the exchange's tail
         gathered = pending.result(copy=False)        # the last exchange is inside the timed region
         assert gathered.shape == (sc.total_streams, nf, 2)
     ev1.record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    if pending is not None:
+        tail_ms = ev_last.elapsed_time(ev1)
     if sampler is not None:
         sampler.sample()
     D.barrier()
-    return {"ms": ev0.elapsed_time(ev1), "t0": t0, "t1": t1, "launches": ctx.kernel_launches - launches0, "warmup": w}
+    return {"ms": ev0.elapsed_time(ev1), "t0": t0, "t1": t1, "launches": ctx.kernel_launches - launches0, "warmup": w,
+            "tail_ms": tail_ms}
 
 
 def single_launch_us(torch, ctx, d_in, ns, nf, out, reps):
@@ -401,6 +407,13 @@ def run_ours(args):
     launches = r["launches"]
     per_rank_ms = D.gather(r["ms"])
     total_ms = max(per_rank_ms)
+    per_rank_tail_us = [1e3 * x for x in D.gather(r["tail_ms"])]
+    # N > 1: the same K steps WITHOUT the exchange on every GPU at once -- what each GPU does on its own in this run, so
+    # that the cost of the exchange and the spread between the GPUs can be told apart
+    per_rank_plain_us = None
+    if world > 1:
+        rp = timed_steps(torch, D, sc, d_in, nf, out, args.steps, 3, exchange=False)
+        per_rank_plain_us = [1e3 * x / args.steps for x in D.gather(rp["ms"])]
     # average duration of one step over the timed region (one fused launch per step; the 2-word-per-frame memset of the
     # summary and, at N > 1, the pushes and the final collect are inside it, so this is an upper bound of the kernel's
     # own time) and the same launch bracketed by its own event pair, outside the timed region
@@ -574,6 +587,12 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "per_rank_ms": {"min": min(per_rank_ms), "max": max(per_rank_ms), "all": per_rank_ms},
     }
+    if world > 1:
+        line["exchange_cost"] = {
+            "plain_step_us_per_rank": per_rank_plain_us, "tail_us_per_rank": per_rank_tail_us,
+            "what": "plain = the same K steps without the exchange, all GPUs at once (no gate, no pushes, no final collect); "
+                    "tail = last fused kernel's end -> table of the last step in hand (inside the timed region, once)",
+            "us_per_step_over_slowest_gpu_alone": step_us - max(per_rank_plain_us)}
     if world > 1:
         line["notes"]["summary_exchange"] = ("peer-memory pushes over NVLink (lv_exchange_*), no per-step collective; GPUs "
                                              "aligned by lv_exchange_gate in front of the first event"

@@ -354,6 +354,8 @@ LV_API int lv_exchange_publish(lv_exchange *x, uint64_t step, const uint32_t *d_
 LV_API int lv_exchange_collect(lv_exchange *x, uint64_t step, uint32_t *d_table, void *cuda_stream);
 LV_API int lv_exchange_error(lv_exchange *x);
 LV_API int lv_exchange_gate(lv_exchange *x, void *cuda_stream);
+/* diagnostics: host-mapped GPU time stamps (ns) of the newest step's push / collect kernels; see csrc/lv_exchange.cu */
+LV_API const unsigned long long *lv_exchange_trace(lv_exchange *x);
 LV_API int lv_exchange_wait_summary(lv_exchange *x, uint64_t step, void *cuda_stream);
 LV_API const char *lv_exchange_last_error(void);
 

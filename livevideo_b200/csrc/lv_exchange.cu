@@ -177,46 +177,63 @@ __device__ void publish_block(const Peers &peers, const Layout &L, int rank, uns
     }
 }
 
-// Whole block.  Wait until every word of ring slot `slot` carries the sequence number of `step`, copy the values to `out`
-// (world x slot_words u32, may be NULL), then retire the step at every rank.
-__device__ void collect_block(const Peers &peers, const Layout &L, int rank, unsigned long long step, int slot, uint32_t *out,
-                              uint32_t *err_host, int *ok)
+// Whole block.  For each of the n_steps steps from `step` on, in order: wait until every word of the step's ring slot
+// carries its sequence number, copy the values out (world x slot_words u32; `out` = one table, or `ring` = the base of a
+// ring of `depth` tables indexed by slot; both may be NULL), then retire the step at every rank.  Several lagged steps
+// cost one launch, not one each.
+__device__ void collect_block(const Peers &peers, const Layout &L, int rank, unsigned long long step, int n_steps, uint32_t *out,
+                              uint32_t *ring, uint32_t *err_host, int *ok)
 {
     unsigned long long *local = peers.p[rank];
     const Waiter wt = begin_wait(local, L, ok);
     const size_t n = (size_t)L.world * L.slot_words;
-    const unsigned long long *src = local + (size_t)slot * n;
-    const uint32_t want = seq_of(step);
-    for (size_t i = threadIdx.x; i < n && wt.alive(); i += blockDim.x) {
-        unsigned long long v = ld_volatile64(src + i);
-        while ((uint32_t)(v >> 32) != want) {
-            if (!wt.pause()) break;
-            v = ld_volatile64(src + i);
+    for (int s = 0; s < n_steps; s++, step++) {
+        const int slot = (int)(step % (unsigned long long)L.depth);
+        const unsigned long long *src = local + (size_t)slot * n;
+        uint32_t *dst = ring ? ring + (size_t)slot * n : out;
+        const uint32_t want = seq_of(step);
+        for (size_t i = threadIdx.x; i < n && wt.alive(); i += blockDim.x) {
+            unsigned long long v = ld_volatile64(src + i);
+            while ((uint32_t)(v >> 32) != want) {
+                if (!wt.pause()) break;
+                v = ld_volatile64(src + i);
+            }
+            if (dst) dst[i] = (uint32_t)v;
         }
-        if (out) out[i] = (uint32_t)v;
+        __syncthreads();
+        if (!*ok) {
+            if (threadIdx.x == 0) raise_err(local, L, err_host, 2u);
+            return;
+        }
+        // retire: the slot may be overwritten once every rank has said so (all loads above have returned)
+        const uint32_t done = (uint32_t)(step + 1ull);
+        for (int r = threadIdx.x; r < L.world; r += blockDim.x) st_volatile32(ack_of(peers.p[r], L) + rank, done);
     }
-    __syncthreads();
-    if (!*ok) {
-        if (threadIdx.x == 0) raise_err(local, L, err_host, 2u);
-        return;
-    }
-    // retire: the slot may be overwritten once every rank has said so (all loads above have returned)
-    const uint32_t done = (uint32_t)(step + 1ull);
-    for (int r = threadIdx.x; r < L.world; r += blockDim.x) st_volatile32(ack_of(peers.p[r], L) + rank, done);
 }
 
+// `trace` (NULL unless lv_exchange_trace was asked for): globaltimer stamps of the newest step, host-mapped --
+// [0] publish entry, [1] publish exit, [2] collect entry, [3] collect exit, [4] end of the fused kernel (k_stamp)
 __global__ void __launch_bounds__(256) k_publish(Peers peers, Layout L, int rank, unsigned long long step, int slot,
-                                                 const uint32_t *src, int n_words, uint32_t *local_copy, uint32_t *err_host)
+                                                 const uint32_t *src, int n_words, uint32_t *local_copy, uint32_t *err_host,
+                                                 unsigned long long *trace)
 {
     __shared__ int ok;
+    if (trace && threadIdx.x == 0) trace[0] = now_ns();
     publish_block(peers, L, rank, step, slot, src, n_words, local_copy, err_host, &ok);
+    __syncthreads();
+    if (trace && threadIdx.x == 0) trace[1] = now_ns();
 }
 
-__global__ void __launch_bounds__(256) k_collect(Peers peers, Layout L, int rank, unsigned long long step, int slot, uint32_t *out,
-                                                 uint32_t *err_host)
+__global__ void k_stamp(unsigned long long *dst) { *dst = now_ns(); }
+
+__global__ void __launch_bounds__(256) k_collect(Peers peers, Layout L, int rank, unsigned long long step, int n_steps, uint32_t *out,
+                                                 uint32_t *ring, uint32_t *err_host, unsigned long long *trace)
 {
     __shared__ int ok;
-    collect_block(peers, L, rank, step, slot, out, err_host, &ok);
+    if (trace && threadIdx.x == 0) trace[2] = now_ns();
+    collect_block(peers, L, rank, step, n_steps, out, ring, err_host, &ok);
+    __syncthreads();
+    if (trace && threadIdx.x == 0) trace[3] = now_ns();
 }
 
 // Device-side rendezvous of all ranks IN the caller's stream: lane r tells rank r "I have reached gate number `count`",
@@ -258,6 +275,7 @@ struct lv_exchange {
     int lag = 0;                           // step k's table is collected when step k+lag is issued (or on result)
     uint32_t *h_err = nullptr;             // host-mapped mirror of the err word (read by the host without a copy)
     uint32_t gates = 0;                    // lv_exchange_gate calls so far
+    unsigned long long *trace = nullptr;   // host-mapped time stamps of the newest step (lv_exchange_trace), else NULL
 };
 
 namespace {
@@ -342,7 +360,25 @@ void lv_exchange_destroy(lv_exchange *x)
     cudaFree(x->own);
     cudaFree(x->local);
     if (x->h_err) cudaFreeHost(x->h_err);
+    if (x->trace) cudaFreeHost(x->trace);
     delete x;
+}
+
+/* Diagnostics: 8 host-mapped u64 GPU-globaltimer stamps (ns) of the newest step -- [0] push kernel entry, [1] exit,
+ * [2] collect kernel entry, [3] exit, [4] end of the fused kernel (a one-thread kernel behind it, only while tracing).
+ * Returns NULL on failure.  Costs one extra launch per step: never enable it in a measured run. */
+const unsigned long long *lv_exchange_trace(lv_exchange *x)
+{
+    if (!x) return nullptr;
+    if (!x->trace) {
+        DevGuard g(x->device);
+        if (cudaHostAlloc(reinterpret_cast<void **>(&x->trace), 8 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess) {
+            x->trace = nullptr;
+            return nullptr;
+        }
+        memset(x->trace, 0, 8 * sizeof(unsigned long long));
+    }
+    return x->trace;
 }
 
 void *lv_exchange_buffer(lv_exchange *x) { return x ? x->local : nullptr; }
@@ -400,7 +436,7 @@ int lv_exchange_publish(lv_exchange *x, uint64_t step, const uint32_t *d_block, 
     if (!x->connected || x->stepping || step != x->published) return LV_E_STATE;      // steps are published in order, once
     DevGuard g(x->device);
     k_publish<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, step, (int)(step % (uint64_t)x->L.depth), d_block,
-                                                        n_words, nullptr, x->h_err);
+                                                        n_words, nullptr, x->h_err, x->trace);
     X_CUDA(cudaGetLastError());
     x->published++;
     return LV_OK;
@@ -413,8 +449,7 @@ int lv_exchange_collect(lv_exchange *x, uint64_t step, uint32_t *d_table, void *
     // steps are collected in order, once, and only after this rank has published its own block of that step
     if (!x->connected || x->stepping || step != x->collected || step >= x->published) return LV_E_STATE;
     DevGuard g(x->device);
-    k_collect<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, step, (int)(step % (uint64_t)x->L.depth), d_table,
-                                                        x->h_err);
+    k_collect<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, step, 1, d_table, nullptr, x->h_err, x->trace);
     X_CUDA(cudaGetLastError());
     x->collected++;
     return LV_OK;
@@ -476,13 +511,11 @@ int ensure_step_state(lv_exchange *x)
 
 int collect_through(lv_exchange *x, uint64_t step)
 {
-    while (x->collected <= step) {
-        const uint64_t j = x->collected;
-        const int slot = (int)(j % (uint64_t)x->L.depth);
-        k_collect<<<1, 256, 0, x->side>>>(x->peers, x->L, x->rank, j, slot, x->tables + (size_t)slot * x->world * x->L.slot_words,
-                                          x->h_err);
+    if (x->collected <= step) {          // every outstanding step up to `step` in ONE launch
+        k_collect<<<1, 256, 0, x->side>>>(x->peers, x->L, x->rank, x->collected, (int)(step + 1 - x->collected), nullptr, x->tables,
+                                          x->h_err, x->trace);
         X_CUDA(cudaGetLastError());
-        x->collected = j + 1;
+        x->collected = step + 1;
     }
     return LV_OK;
 }
@@ -521,7 +554,8 @@ int lv_exchange_step(lv_exchange *x, lv_ctx *ctx, const uint8_t *d_i420, int fir
     }
     X_CUDA(cudaEventRecord(x->ev_kernel[slot], st));
     X_CUDA(cudaStreamWaitEvent(x->side, x->ev_kernel[slot], 0));
-    k_publish<<<1, 256, 0, x->side>>>(x->peers, x->L, x->rank, k, slot, block, (int)n_words, d_summary, x->h_err);
+    if (x->trace) k_stamp<<<1, 1, 0, st>>>(x->trace + 4);
+    k_publish<<<1, 256, 0, x->side>>>(x->peers, x->L, x->rank, k, slot, block, (int)n_words, d_summary, x->h_err, x->trace);
     X_CUDA(cudaGetLastError());
     X_CUDA(cudaEventRecord(x->ev_pushed[slot], x->side));
     x->published = k + 1;

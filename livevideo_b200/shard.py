@@ -125,9 +125,11 @@ class PeerExchange:
         capi.check(capi.lib().lv_exchange_create(device, rank, world, depth, slot_words, C.byref(self._h)),
                    "lv_exchange_create")
         self.device, self.rank, self.world, self.slot_words, self.depth = device, rank, world, slot_words, depth
+        self._views = {}
 
     def close(self):
         if self._h:
+            self._views = {}
             self._capi.lib().lv_exchange_destroy(self._h)
             self._h = self._C.c_void_p()
 
@@ -215,12 +217,16 @@ class PeerExchange:
     def result(self, step, copy=True):
         """int32 CUDA tensor [world, slot_words]: the table of `step` (blocks until every block has arrived).
         copy=False returns a view of the exchange's own ring slot, valid until `depth` further steps are issued."""
-        from .api import _DevView
         p = self._C.c_void_p()
         self._capi.check(self._capi.lib().lv_exchange_result(self._h, step, self._C.byref(p)), "lv_exchange_result")
-        nbytes = 4 * self.world * self.slot_words
-        import torch
-        t = _DevView(p.value, nbytes, self.device).tensor().view(torch.int32).reshape(self.world, self.slot_words)
+        t = self._views.get(p.value)
+        if t is None:       # one tensor view per ring slot, made once (wrapping device memory costs tens of microseconds)
+            import torch
+
+            from .api import _DevView
+            nbytes = 4 * self.world * self.slot_words
+            t = _DevView(p.value, nbytes, self.device).tensor().view(torch.int32).reshape(self.world, self.slot_words)
+            self._views[p.value] = t
         return t.clone() if copy else t
 
 

@@ -42,6 +42,6 @@ for f in sorted(glob.glob("gpurun_out/scale_*.json")):
             e = d.get("e2e", {})
             print(f.split("scale_")[1][:-5], "N", d["n_gpus"], "steps", d["steps"], round(d["value"]), "Mpx/s", round(d["ms_per_step"] * 1e3, 1), "us/step",
                   "kernel", round(d["roofline"]["kernel_us_single_launch_events"], 1), "per-rank ms", [round(x, 3) for x in d.get("per_rank_ms", {}).get("all", [])],
-                  "e2e", round(e.get("value", 0)), "ceil", round(e.get("link_ceiling", {}).get("mpx_s_ceiling", 0)), d["clocks"]["reasons"],
+                  "xc", d.get("exchange_cost", {}), "e2e", round(e.get("value", 0)), "ceil", round(e.get("link_ceiling", {}).get("mpx_s_ceiling", 0)), d["clocks"]["reasons"],
                   {k: (round(v.get("value", 0)), round(v.get("efficiency_vs_single_gpu_same_run", 0), 3)) for k, v in (d.get("also") or {}).items()})
 PY
