@@ -282,13 +282,17 @@ def timed_steps(torch, D, sc, d_in, nf, out, steps, warmup, sampler=None, exchan
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.kernel_launches
     if multi:
-        sc.gate()
+        # held gate: a rank counts as arrived only once its host has the first step enqueued (gate_open below), so no GPU
+        # starts its K steps late merely because its host process was the last one out of the barrier
+        sc.gate(hold=True)
     # The timed region holds nothing but the K steps: two events on the launching stream, no per-step events (an
     # event pair between back-to-back launches costs ~5 us per step on this kernel: 119 us vs 114 us).
     t0 = time.perf_counter()
     ev0.record()
-    for _ in range(steps):
+    for i in range(steps):
         pending = one()
+        if multi and i == 0:
+            sc.gate_open()
     tail_ms = 0.0
     if pending is not None:
         ev_last = torch.cuda.Event(enable_timing=True)

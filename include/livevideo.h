@@ -329,7 +329,10 @@ LV_API int lv_device_sm_count(const lv_ctx *ctx);
  *                          later kernel returns at once; read from a host-mapped word, no copy, no synchronisation
  *   lv_exchange_gate       device-side rendezvous of all ranks in the caller's stream (collective: same number of calls
  *                          on every rank): what is enqueued behind it starts within microseconds of the same instant on
- *                          every GPU, however far apart the host threads are
+ *                          every GPU, however far apart the host threads are.  hold != 0: this rank announces its arrival
+ *                          only after lv_exchange_gate_open -- call that once the work behind the gate is enqueued, and
+ *                          when the gate opens every GPU has its work in the queue (no GPU starts late because its host
+ *                          was the last to launch)
  *   lv_exchange_wait_summary  makes a stream wait until the caller's d_summary of `step` has been written: with
  *                          lv_exchange_step that buffer is filled by the push kernel on the exchange's own stream (NOT
  *                          in-stream behind the fused kernel as in lv_convert_diff_batch); a consumer on the compute
@@ -353,7 +356,8 @@ LV_API int lv_exchange_result(lv_exchange *x, uint64_t step, const uint32_t **d_
 LV_API int lv_exchange_publish(lv_exchange *x, uint64_t step, const uint32_t *d_block, int n_words, void *cuda_stream);
 LV_API int lv_exchange_collect(lv_exchange *x, uint64_t step, uint32_t *d_table, void *cuda_stream);
 LV_API int lv_exchange_error(lv_exchange *x);
-LV_API int lv_exchange_gate(lv_exchange *x, void *cuda_stream);
+LV_API int lv_exchange_gate(lv_exchange *x, void *cuda_stream, int hold);
+LV_API int lv_exchange_gate_open(lv_exchange *x);
 /* diagnostics: host-mapped GPU time stamps (ns) of the newest step's push / collect kernels; see csrc/lv_exchange.cu */
 LV_API const unsigned long long *lv_exchange_trace(lv_exchange *x);
 LV_API int lv_exchange_wait_summary(lv_exchange *x, uint64_t step, void *cuda_stream);

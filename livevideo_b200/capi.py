@@ -80,7 +80,8 @@ SYMBOLS = {
     "lv_exchange_publish": (C.c_int, [_vp, C.c_uint64, _vp, C.c_int, _vp]),
     "lv_exchange_collect": (C.c_int, [_vp, C.c_uint64, _vp, _vp]),
     "lv_exchange_error": (C.c_int, [_vp]),
-    "lv_exchange_gate": (C.c_int, [_vp, _vp]),
+    "lv_exchange_gate": (C.c_int, [_vp, _vp, C.c_int]),
+    "lv_exchange_gate_open": (C.c_int, [_vp]),
     "lv_exchange_trace": (C.POINTER(C.c_uint64), [_vp]),
     "lv_exchange_wait_summary": (C.c_int, [_vp, C.c_uint64, _vp]),
     "lv_exchange_step": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -36,6 +36,7 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -171,9 +172,13 @@ __device__ void publish_block(const Peers &peers, const Layout &L, int rank, uns
     const unsigned long long seq = (unsigned long long)seq_of(step) << 32;
     for (int r = warp; r < L.world; r += nwarps) {
         unsigned long long *dst = peers.p[r] + row;
-        for (int i = lane; i < L.slot_words; i += 32) st_volatile64(dst + i, seq | (i < n_words ? src[i] : 0u));
-        if (r == rank && local_copy && local_copy != src)       // the caller's own summary buffer gets its usual content
+        if (r == rank && local_copy && local_copy != src) {
+            // the caller's own summary buffer gets its usual content BEFORE this rank's words appear in its own table:
+            // a complete table of step k (lv_exchange_result) then implies that d_summary of step k is in place
             for (int i = lane; i < n_words; i += 32) local_copy[i] = src[i];
+            __threadfence();
+        }
+        for (int i = lane; i < L.slot_words; i += 32) st_volatile64(dst + i, seq | (i < n_words ? src[i] : 0u));
     }
 }
 
@@ -182,7 +187,7 @@ __device__ void publish_block(const Peers &peers, const Layout &L, int rank, uns
 // ring of `depth` tables indexed by slot; both may be NULL), then retire the step at every rank.  Several lagged steps
 // cost one launch, not one each.
 __device__ void collect_block(const Peers &peers, const Layout &L, int rank, unsigned long long step, int n_steps, uint32_t *out,
-                              uint32_t *ring, uint32_t *err_host, int *ok)
+                              uint32_t *ring, uint32_t *err_host, unsigned long long *done_host, int *ok)
 {
     unsigned long long *local = peers.p[rank];
     const Waiter wt = begin_wait(local, L, ok);
@@ -200,11 +205,14 @@ __device__ void collect_block(const Peers &peers, const Layout &L, int rank, uns
             }
             if (dst) dst[i] = (uint32_t)v;
         }
+        __threadfence_system();          // the table is complete for every later reader, on the device or the host ...
         __syncthreads();
         if (!*ok) {
             if (threadIdx.x == 0) raise_err(local, L, err_host, 2u);
             return;
         }
+        // ... before the host is told (it polls this host-mapped word instead of synchronising the stream)
+        if (done_host && threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(done_host) = step + 1ull;
         // retire: the slot may be overwritten once every rank has said so (all loads above have returned)
         const uint32_t done = (uint32_t)(step + 1ull);
         for (int r = threadIdx.x; r < L.world; r += blockDim.x) st_volatile32(ack_of(peers.p[r], L) + rank, done);
@@ -227,11 +235,12 @@ __global__ void __launch_bounds__(256) k_publish(Peers peers, Layout L, int rank
 __global__ void k_stamp(unsigned long long *dst) { *dst = now_ns(); }
 
 __global__ void __launch_bounds__(256) k_collect(Peers peers, Layout L, int rank, unsigned long long step, int n_steps, uint32_t *out,
-                                                 uint32_t *ring, uint32_t *err_host, unsigned long long *trace)
+                                                 uint32_t *ring, uint32_t *err_host, unsigned long long *done_host,
+                                                 unsigned long long *trace)
 {
     __shared__ int ok;
     if (trace && threadIdx.x == 0) trace[2] = now_ns();
-    collect_block(peers, L, rank, step, n_steps, out, ring, err_host, &ok);
+    collect_block(peers, L, rank, step, n_steps, out, ring, err_host, done_host, &ok);
     __syncthreads();
     if (trace && threadIdx.x == 0) trace[3] = now_ns();
 }
@@ -239,11 +248,18 @@ __global__ void __launch_bounds__(256) k_collect(Peers peers, Layout L, int rank
 // Device-side rendezvous of all ranks IN the caller's stream: lane r tells rank r "I have reached gate number `count`",
 // then waits until rank r has said the same here.  Everything enqueued behind it starts within a few microseconds of
 // the same instant on every GPU (the hosts may be milliseconds apart).
-__global__ void __launch_bounds__(32) k_gate(Peers peers, Layout L, int rank, uint32_t count, uint32_t *err_host)
+//   `hold` (host-mapped, optional): first wait until the host has written `count` there (lv_exchange_gate_open) -- a rank
+//   tells its peers that it has arrived only when its own host has the work behind the gate enqueued, so when the gate
+//   opens EVERY GPU has that work in its queue.
+__global__ void __launch_bounds__(32) k_gate(Peers peers, Layout L, int rank, uint32_t count, const uint32_t *hold, uint32_t *err_host)
 {
     __shared__ int ok;
     unsigned long long *local = peers.p[rank];
     const Waiter wt = begin_wait(local, L, &ok);
+    if (hold && threadIdx.x == 0)
+        while ((int32_t)(*reinterpret_cast<const volatile uint32_t *>(hold) - count) < 0)
+            if (!wt.pause()) break;
+    __syncthreads();
     for (int r = threadIdx.x; r < L.world; r += 32) st_volatile32(gate_of(peers.p[r], L) + rank, count);
     for (int r = threadIdx.x; r < L.world && wt.alive(); r += 32) {
         const uint32_t *g = gate_of(local, L) + r;
@@ -265,7 +281,10 @@ struct lv_exchange {
     bool connected = false;
     uint64_t published = 0, collected = 0; // steps whose publish / collect has been enqueued
     // lv_exchange_step
-    cudaStream_t side = nullptr;           // the pushes / collects run here, never in the caller's stream
+    cudaStream_t side = nullptr;           // the pushes run here, never in the caller's stream
+    cudaStream_t coll = nullptr;           // the collects run here: a collect only reads local memory, so it depends on no
+                                           // push of this rank and can already be spinning when the last block arrives
+    unsigned long long *h_done = nullptr;  // host-mapped: number of steps whose table is complete (written by the collects)
     cudaEvent_t *ev_kernel = nullptr;      // [depth] fused kernel of the step in this ring slot has finished
     cudaEvent_t *ev_pushed = nullptr;      // [depth] the push of the step in this ring slot has read its row
     uint32_t *tables = nullptr;            // ring of collected tables: depth x world x slot_words
@@ -275,6 +294,7 @@ struct lv_exchange {
     int lag = 0;                           // step k's table is collected when step k+lag is issued (or on result)
     uint32_t *h_err = nullptr;             // host-mapped mirror of the err word (read by the host without a copy)
     uint32_t gates = 0;                    // lv_exchange_gate calls so far
+    uint32_t *h_go = nullptr;              // host-mapped: number of gates the host has opened (lv_exchange_gate_open)
     unsigned long long *trace = nullptr;   // host-mapped time stamps of the newest step (lv_exchange_trace), else NULL
 };
 
@@ -327,11 +347,14 @@ int lv_exchange_create(int device, int rank, int world, int depth, int slot_word
     if (e == cudaSuccess) e = cudaMemset(x->local, 0, bytes);       // sequence number 0 = "nothing has arrived"
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&x->h_err), sizeof(uint32_t), cudaHostAllocMapped);
     if (e == cudaSuccess) *x->h_err = 0u;
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&x->h_done), sizeof(unsigned long long), cudaHostAllocMapped);
+    if (e == cudaSuccess) *x->h_done = 0ull;
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         int rc = x_fail(e, "exchange buffer");
         cudaFree(x->local);
         if (x->h_err) cudaFreeHost(x->h_err);
+        if (x->h_done) cudaFreeHost(x->h_done);
         delete x;
         return rc;
     }
@@ -356,10 +379,13 @@ void lv_exchange_destroy(lv_exchange *x)
     delete[] x->ev_kernel;
     delete[] x->ev_pushed;
     if (x->side) cudaStreamDestroy(x->side);
+    if (x->coll) cudaStreamDestroy(x->coll);
     cudaFree(x->tables);
     cudaFree(x->own);
     cudaFree(x->local);
     if (x->h_err) cudaFreeHost(x->h_err);
+    if (x->h_done) cudaFreeHost(x->h_done);
+    if (x->h_go) cudaFreeHost(x->h_go);
     if (x->trace) cudaFreeHost(x->trace);
     delete x;
 }
@@ -449,7 +475,7 @@ int lv_exchange_collect(lv_exchange *x, uint64_t step, uint32_t *d_table, void *
     // steps are collected in order, once, and only after this rank has published its own block of that step
     if (!x->connected || x->stepping || step != x->collected || step >= x->published) return LV_E_STATE;
     DevGuard g(x->device);
-    k_collect<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, step, 1, d_table, nullptr, x->h_err, x->trace);
+    k_collect<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, step, 1, d_table, nullptr, x->h_err, nullptr, x->trace);
     X_CUDA(cudaGetLastError());
     x->collected++;
     return LV_OK;
@@ -466,14 +492,29 @@ int lv_exchange_error(lv_exchange *x)
 
 /* Device-side rendezvous in `cuda_stream`: work enqueued behind it starts on every rank within microseconds of the same
  * instant, however far apart the host threads are.  Collective: every rank calls it the same number of times. */
-int lv_exchange_gate(lv_exchange *x, void *cuda_stream)
+int lv_exchange_gate(lv_exchange *x, void *cuda_stream, int hold)
 {
     if (!x) return LV_E_ARG;
     if (!x->connected) return LV_E_STATE;
     DevGuard g(x->device);
+    if (hold && !x->h_go) {
+        X_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&x->h_go), sizeof(uint32_t), cudaHostAllocMapped));
+        *x->h_go = x->gates;                 // every earlier gate counts as opened
+    }
     x->gates++;
-    k_gate<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, x->gates, x->h_err);
+    if (!hold && x->h_go) *reinterpret_cast<volatile uint32_t *>(x->h_go) = x->gates;
+    k_gate<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(x->peers, x->L, x->rank, x->gates, hold ? x->h_go : nullptr, x->h_err);
     X_CUDA(cudaGetLastError());
+    return LV_OK;
+}
+
+/* Opens the newest held gate of this rank (see lv_exchange_gate).  A held gate that is never opened gives up after 4 s
+ * (lv_exchange_error 3). */
+int lv_exchange_gate_open(lv_exchange *x)
+{
+    if (!x) return LV_E_ARG;
+    if (!x->h_go) return LV_E_STATE;
+    *reinterpret_cast<volatile uint32_t *>(x->h_go) = x->gates;
     return LV_OK;
 }
 
@@ -496,7 +537,11 @@ int ensure_step_state(lv_exchange *x)
 {
     if (x->side) return LV_OK;
     const int d = x->L.depth;
-    X_CUDA(cudaStreamCreateWithFlags(&x->side, cudaStreamNonBlocking));
+    // highest priority: their one-block kernels are dispatched ahead of the fused kernel's remaining blocks
+    int prio_lo = 0, prio_hi = 0;
+    X_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    X_CUDA(cudaStreamCreateWithPriority(&x->side, cudaStreamNonBlocking, prio_hi));
+    X_CUDA(cudaStreamCreateWithPriority(&x->coll, cudaStreamNonBlocking, prio_hi));
     x->ev_kernel = new (std::nothrow) cudaEvent_t[d]();
     x->ev_pushed = new (std::nothrow) cudaEvent_t[d]();
     if (!x->ev_kernel || !x->ev_pushed) return LV_E_NOMEM;
@@ -511,9 +556,9 @@ int ensure_step_state(lv_exchange *x)
 
 int collect_through(lv_exchange *x, uint64_t step)
 {
-    if (x->collected <= step) {          // every outstanding step up to `step` in ONE launch
-        k_collect<<<1, 256, 0, x->side>>>(x->peers, x->L, x->rank, x->collected, (int)(step + 1 - x->collected), nullptr, x->tables,
-                                          x->h_err, x->trace);
+    if (x->collected <= step) {          // every outstanding step up to `step` in ONE launch, on the collects' own stream
+        k_collect<<<1, 256, 0, x->coll>>>(x->peers, x->L, x->rank, x->collected, (int)(step + 1 - x->collected), nullptr, x->tables,
+                                          x->h_err, x->h_done, x->trace);
         X_CUDA(cudaGetLastError());
         x->collected = step + 1;
     }
@@ -582,7 +627,25 @@ int lv_exchange_result(lv_exchange *x, uint64_t step, const uint32_t **d_table)
     DevGuard g(x->device);
     int rc = collect_through(x, step);
     if (rc != LV_OK) return rc;
-    X_CUDA(cudaStreamSynchronize(x->side));
+    // The collect kernel tells the host through a host-mapped word: no stream synchronisation on the way out (a collect
+    // never spins for more than 4 s, so neither does this loop -- 6 s covers a kernel that could not even start).
+    {
+        const volatile unsigned long long *done = x->h_done;
+        const volatile uint32_t *errw = x->h_err;
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned spins = 0;
+        while (*done < step + 1 && *errw == 0u) {
+            if ((++spins & 0x3ffu) == 0) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(6)) {
+                    snprintf(x_err, sizeof x_err, "peer exchange: the table of step %llu did not complete within 6 s",
+                             (unsigned long long)step);
+                    return LV_E_STATE;
+                }
+                const cudaError_t q = cudaStreamQuery(x->coll);     // a failed launch or a dead context must not spin here
+                if (q != cudaSuccess && q != cudaErrorNotReady) return x_fail(q, "collect stream");
+            }
+        }
+    }
     const int err = lv_exchange_error(x);
     if (err != 0) {
         snprintf(x_err, sizeof x_err, "peer exchange gave up waiting for a peer (%s)",

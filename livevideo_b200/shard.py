@@ -205,9 +205,13 @@ class PeerExchange:
         """Push the newest step's block now (it otherwise travels in front of the next step); asynchronous."""
         self._capi.check(self._capi.lib().lv_exchange_flush(self._h), "lv_exchange_flush")
 
-    def gate(self, stream):
-        """lv_exchange_gate: device-side rendezvous of all ranks in `stream` (collective)."""
-        self._capi.check(self._capi.lib().lv_exchange_gate(self._h, stream.cuda_stream), "lv_exchange_gate")
+    def gate(self, stream, hold=False):
+        """lv_exchange_gate: device-side rendezvous of all ranks in `stream` (collective).  hold=True: this rank counts as
+        arrived only after gate_open() -- call it once the work behind the gate is enqueued."""
+        self._capi.check(self._capi.lib().lv_exchange_gate(self._h, stream.cuda_stream, 1 if hold else 0), "lv_exchange_gate")
+
+    def gate_open(self):
+        self._capi.check(self._capi.lib().lv_exchange_gate_open(self._h), "lv_exchange_gate_open")
 
     def wait_summary(self, step, stream):
         """lv_exchange_wait_summary: `stream` waits until the caller's d_summary of `step` has been written."""
@@ -359,17 +363,27 @@ class ShardedContext:
                                     n_frames, group=group)
         return None
 
-    def gate(self, group=None):
+    def gate(self, group=None, hold=False):
         """Align the GPUs of all ranks: what is enqueued on the current stream after this call starts within microseconds
         of the same instant on every rank, however far apart the host processes are.  Peer exchange: one tiny kernel
-        that signals and waits over NVLink (lv_exchange_gate); otherwise an all-reduce of one word on the stream."""
+        that signals and waits over NVLink (lv_exchange_gate); otherwise an all-reduce of one word on the stream.
+        hold=True (peer exchange only): the gate opens only after every rank has called gate_open(), i.e. when every GPU
+        already has the work behind the gate in its queue."""
         import torch
         import torch.distributed as dist
+        self._held = False
         if self.exchange is not None:
-            self.exchange.gate(torch.cuda.current_stream(self.device))
+            self.exchange.gate(torch.cuda.current_stream(self.device), hold=hold)
+            self._held = hold
         elif self.world > 1 and dist.is_available() and dist.is_initialized():
             t = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", self.device))
             dist.all_reduce(t, group=group)
+
+    def gate_open(self):
+        """Open a gate taken with hold=True (no-op otherwise)."""
+        if getattr(self, "_held", False):
+            self.exchange.gate_open()
+            self._held = False
 
     def step_async(self, i420_local, n_frames, out, group=None):
         """Fused kernel, then the summary all-gather started WITHOUT blocking the compute stream: the returned

@@ -21,39 +21,7 @@
  * buffers that his hooks in the macroblock decoder write unconditionally (curr_frm, curr_res:
  * lib/JM/macroblock.c:3916-3936, 6025-6069; allocated by CMainDlg::AllocBuf in the application).
  */
-#include <fcntl.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-#include <unistd.h>
-
-#include "global.h"
-#include "annexb.h"
-#include "erc_api.h"
-#include "fmo.h"
-#include "image.h"
-#include "mbuffer.h"
-#include "memalloc.h"
-#include "output.h"
-
-extern FILE *bitss;                 /* lib/JM/annexb.c:28: the stream handle GetAnnexbNALU reads */
-extern objectBuffer_t *erc_object_list;
-extern ercVariables_t *erc_errorVar;
-extern ColocatedParams *Co_located;
-extern int tot_time;
-
-static unsigned char ***alloc3(int h, int w, int c)
-{
-    unsigned char ***p = (unsigned char ***)calloc((size_t)h, sizeof(unsigned char **));
-    unsigned char **rows = (unsigned char **)calloc((size_t)h * w, sizeof(unsigned char *));
-    unsigned char *data = (unsigned char *)calloc((size_t)h * w * c, 1);
-    int i, j;
-    for (i = 0; i < h; i++) {
-        p[i] = rows + (size_t)i * w;
-        for (j = 0; j < w; j++) p[i][j] = data + ((size_t)i * w + j) * c;
-    }
-    return p;
-}
+#include "jm_driver.h"
 
 void img2buf(imgpel **imgX, unsigned char *buf, int size_x, int size_y, int symbol_size_in_bytes, int crop_left,
              int crop_right, int crop_top, int crop_bottom);          /* lib/JM/output.c:87 */
@@ -100,83 +68,21 @@ static int nearlyzero_mode(void)
 
 int main(int argc, char **argv)
 {
-    int w, h, mbs;
+    int fd, rc;
     if (argc == 8 && strcmp(argv[1], "--img2buf") == 0) return img2buf_mode(argv + 2);
     if (argc == 2 && strcmp(argv[1], "--nearlyzero") == 0) return nearlyzero_mode();
     if (argc < 5) {
         fprintf(stderr, "usage: %s stream.264 out.yuv|- width height\n", argv[0]);
         return 2;
     }
-    w = atoi(argv[3]);
-    h = atoi(argv[4]);
-    h = (h + 15) / 16 * 16;                       /* coded size: whole macroblocks */
-    w = (w + 15) / 16 * 16;
-    mbs = (w / 16) * (h / 16);
-
-    input = (struct inp_par *)calloc(1, sizeof(struct inp_par));
-    snr = (struct snr_par *)calloc(1, sizeof(struct snr_par));
-    img = (struct img_par *)calloc(1, sizeof(struct img_par));
-    if (!input || !snr || !img) return 3;
-
-    /* MainDlg.cpp:313-321 */
-    strcpy(input->infile, argv[1]);
-    strcpy(input->outfile, argv[2]);
-    strcpy(input->reffile, "/nonexistent_ref.yuv");
-    input->FileFormat = PAR_OF_ANNEXB;
-    input->ref_offset = 0;
-    input->poc_scale = 2;                          /* bin/decoder.cfg line 7 */
-    input->write_uv = 1;
-    img->conceal_mode = input->conceal_mode = 0;   /* decoder.cfg: error concealment off */
-    img->ref_poc_gap = input->ref_poc_gap = 2;
-    img->poc_gap = input->poc_gap = 2;
-
-    /* the analysis globals of lib/JM/global.h:146-238 that decode paths touch; everything else stays 0 = off */
-    iwidth = w;
-    iheight = h;
-    curr_frm = alloc3(h, w, 3);
-    prev_frm = alloc3(h, w, 3);
-    curr_res = alloc3(h, w, 3);
-    MbType = (int *)calloc((size_t)mbs, sizeof(int));
-    full_decode_flag = 1;
-
-    if (strcmp(argv[2], "-") == 0) p_out = 1;      /* stdout */
-    else if ((p_out = open(input->outfile, O_WRONLY | O_CREAT | O_TRUNC, 0644)) == -1) {
-        perror(input->outfile);
+    if (strcmp(argv[2], "-") == 0) fd = 1;         /* stdout */
+    else if ((fd = open(argv[2], O_WRONLY | O_CREAT | O_TRUNC, 0644)) == -1) {
+        perror(argv[2]);
         return 4;
     }
-    p_ref = -1;
-
-    init_old_slice();
-    OpenBitstreamFile(input->infile);              /* `bits`: read_new_slice calls ftell() on it (image.c:2260) */
-    bitss = fopen(input->infile, "rb");            /* MainDlg.cpp:354-355: the handle GetAnnexbNALU reads */
-    if (!bitss) {
-        perror(input->infile);
-        return 5;
-    }
-
-    /* lib/JM/ldecod.c:243-270 (the commented-out main) */
-    malloc_slice(input, img);
-    init(img);
-    dec_picture = NULL;
-    dpb.init_done = 0;
-    g_nFrame = 0;
-    init_out_buffer();
-    img->idr_psnr_number = input->ref_offset;
-    img->psnr_number = 0;
-    img->number = 0;
-    img->type = I_SLICE;
-    img->dec_ref_pic_marking_buffer = NULL;
-    Bframe_ctr = snr->frame_ctr = 0;
-    tot_time = 0;
-
-    while (decode_one_frame(img, input, snr) != EOS)
-        ;
-
-    flush_dpb();
-#ifdef PAIR_FIELDS_IN_OUTPUT
-    flush_pending_output(p_out);
-#endif
-    fclose(bitss);
-    if (p_out != 1) close(p_out);
+    rc = jmd_open(argv[1], argv[2], fd, atoi(argv[3]), atoi(argv[4]));
+    if (rc) return rc;
+    jmd_decode_all();
+    if (fd != 1) close(fd);
     return 0;
 }

@@ -363,8 +363,9 @@ def _ipc_worker(rank, world, port, q):
             want = orc.convert_diff_batch(frames, prev, S, T, w, h, 20, 0, want_bgr=False, want_mask=False)["summary"]
             d_in = torch.from_numpy(frames[first:first + count].reshape(-1).copy()).cuda()
             if k == 4:
-                sc.gate()                                     # device-side rendezvous, mid-run
+                sc.gate(hold=(rank == 0))                     # device-side rendezvous, mid-run (rank 0 holds its arrival)
             hd = sc.step_async(d_in, T, out)
+            sc.gate_open()                                    # no-op unless a held gate is pending
             if k % 4 == 3 or k == steps - 1:
                 got = hd.result().cpu().numpy().view(np.uint32).reshape(S * T, 2)
                 ok = ok and np.array_equal(got, want)

@@ -69,3 +69,36 @@ def test_config5_chain_small(jm, orc):
     rep = config5_e2e.run(352, 288, 11, 4, check=True)
     assert rep["bit_exact_vs_oracle"] is True
     assert rep["gpu_launches"] >= 3
+
+
+JM_INPROC = os.path.join(ROOT, "oracle", "_ref", "jm_inproc")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,n,batch", [(352, 288, 7, 3), (1920, 1080, 5, 2), (64, 40, 4, 8)])
+def test_inprocess_hook_feeds_real_16bit_pictures(jm, orc, tmp_path, w, h, n, batch):
+    """The reference's decoder and liblivevideo.so in ONE process (oracle/_ref/jm_inproc = JM unmodified, its
+    write_out_picture replaced at link time by tools/jm_hook/jm_inproc.c): every decoded picture's unsigned-short planes
+    (imgpel, lib/JM/global.h:61; 1080p is coded as 1088 rows and cropped, output.c:375-380) are block-copied into a pinned
+    batch and go through lv_step_host_pictures.  BGR, counts, map and summaries must equal the oracle on the generator's
+    frames, bit for bit."""
+    import json
+    import ipcm_stream
+    if not os.path.exists(JM_INPROC):
+        pytest.skip("oracle/_ref/jm_inproc not built (needs the reference tree and liblivevideo.so)")
+    frames = np.stack([orc.gen("camera" if min(w, h) >= 48 else "uniform", 3, 0, t, w, h) for t in range(n)])
+    path = str(tmp_path / "s.264")
+    ipcm_stream.write_stream(path, list(frames), w, h)
+    prefix = str(tmp_path / "out")
+    r = subprocess.run([JM_INPROC, path, str(w), str(h), str(batch), prefix], capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    rep = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    assert rep["frames"] == n and rep["imgpel_bytes"] == 2
+    assert rep["picture"] == [(w + 15) // 16 * 16, (h + 15) // 16 * 16]        # the decoder's own (uncropped) planes
+    assert rep["gpu_launches"] >= 2 * ((n + batch - 1) // batch)               # narrowing + fused kernel per batch
+    prev = np.zeros((1, w * h), np.uint8)
+    ref = orc.convert_diff_batch(frames[None], prev, 1, n, w, h, 20, 0, want_mask=False)
+    assert np.array_equal(np.fromfile(prefix + ".bgr", np.uint8), ref["bgr"])
+    assert np.array_equal(np.fromfile(prefix + ".cnt", np.uint16), ref["mb_count"])
+    assert np.array_equal(np.fromfile(prefix + ".map", np.uint8), ref["mb_map"])
+    assert np.array_equal(np.fromfile(prefix + ".sum", np.uint32).reshape(-1, 2), ref["summary"])
