@@ -278,8 +278,12 @@ def timed_steps(torch, D, sc, d_in, nf, out, steps, warmup, sampler=None, exchan
         pending = one()
     if pending is not None:
         pending.result(copy=False)
+    # the events exist (and have been recorded once) before the region: at N > 1 the closing record sits on the critical
+    # path behind the last table, and a torch event is only created at its first record
+    ev0, ev1, ev_last = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    for e in (ev0, ev1, ev_last):
+        e.record()
     D.barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.kernel_launches
     if multi:
         # held gate: a rank counts as arrived only once its host has the first step enqueued (gate_open below), so no GPU
@@ -293,22 +297,29 @@ def timed_steps(torch, D, sc, d_in, nf, out, steps, warmup, sampler=None, exchan
         pending = one()
         if multi and i == 0:
             sc.gate_open()
-    tail_ms = 0.0
+    tail_ms = host_tail_ms = 0.0
     if pending is not None:
-        ev_last = torch.cuda.Event(enable_timing=True)
         ev_last.record()                             # behind the last fused kernel: what follows is the exchange's tail
-        gathered = pending.result(copy=False)        # the last exchange is inside the timed region
-        assert gathered.shape == (sc.total_streams, nf, 2)
+        # The last exchange is inside the timed region, timed ON THE DEVICE like everything else: the compute stream
+        # waits until the table of the last step is complete (every rank's last block has arrived and been collected) and
+        # the closing event is recorded behind that wait.  The host then picks the table up (result()); how long that
+        # takes after the device is done is a property of the host (reported as tail_host_us), not of the GPUs.
+        pending.wait_table()
     ev1.record()
+    if pending is not None:
+        gathered = pending.result(copy=False)
+        th = time.perf_counter()
+        assert gathered.shape == (sc.total_streams, nf, 2)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     if pending is not None:
         tail_ms = ev_last.elapsed_time(ev1)
+        host_tail_ms = (th - t0) * 1e3              # host clock: first launch -> table in hand
     if sampler is not None:
         sampler.sample()
     D.barrier()
     return {"ms": ev0.elapsed_time(ev1), "t0": t0, "t1": t1, "launches": ctx.kernel_launches - launches0, "warmup": w,
-            "tail_ms": tail_ms}
+            "tail_ms": tail_ms, "host_ms": host_tail_ms}
 
 
 def single_launch_us(torch, ctx, d_in, ns, nf, out, reps):
@@ -412,6 +423,7 @@ def run_ours(args):
     per_rank_ms = D.gather(r["ms"])
     total_ms = max(per_rank_ms)
     per_rank_tail_us = [1e3 * x for x in D.gather(r["tail_ms"])]
+    per_rank_host_ms = D.gather(r["host_ms"])
     # N > 1: the same K steps WITHOUT the exchange on every GPU at once -- what each GPU does on its own in this run, so
     # that the cost of the exchange and the spread between the GPUs can be told apart
     per_rank_plain_us = None
@@ -594,8 +606,10 @@ def run_ours(args):
     if world > 1:
         line["exchange_cost"] = {
             "plain_step_us_per_rank": per_rank_plain_us, "tail_us_per_rank": per_rank_tail_us,
+            "host_first_launch_to_table_in_hand_ms_per_rank": per_rank_host_ms,
             "what": "plain = the same K steps without the exchange, all GPUs at once (no gate, no pushes, no final collect); "
-                    "tail = last fused kernel's end -> table of the last step in hand (inside the timed region, once)",
+                    "tail = last fused kernel's end -> table of the last step complete on the device (inside the timed "
+                    "region, once); host_* = host wall clock from the first launch to result() returning the table",
             "us_per_step_over_slowest_gpu_alone": step_us - max(per_rank_plain_us)}
     if world > 1:
         line["notes"]["summary_exchange"] = ("peer-memory pushes over NVLink (lv_exchange_*), no per-step collective; GPUs "

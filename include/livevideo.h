@@ -361,6 +361,9 @@ LV_API int lv_exchange_gate_open(lv_exchange *x);
 /* diagnostics: host-mapped GPU time stamps (ns) of the newest step's push / collect kernels; see csrc/lv_exchange.cu */
 LV_API const unsigned long long *lv_exchange_trace(lv_exchange *x);
 LV_API int lv_exchange_wait_summary(lv_exchange *x, uint64_t step, void *cuda_stream);
+/* device-side form of lv_exchange_result: `cuda_stream` waits until the table of `step` is complete (no host round
+ * trip: enqueue the kernel that consumes the table behind it); *d_table (optional) as in lv_exchange_result */
+LV_API int lv_exchange_wait_table(lv_exchange *x, uint64_t step, void *cuda_stream, const uint32_t **d_table);
 LV_API const char *lv_exchange_last_error(void);
 
 #ifdef __cplusplus

@@ -84,6 +84,7 @@ SYMBOLS = {
     "lv_exchange_gate_open": (C.c_int, [_vp]),
     "lv_exchange_trace": (C.POINTER(C.c_uint64), [_vp]),
     "lv_exchange_wait_summary": (C.c_int, [_vp, C.c_uint64, _vp]),
+    "lv_exchange_wait_table": (C.c_int, [_vp, C.c_uint64, _vp, C.POINTER(_vp)]),
     "lv_exchange_step": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                    C.POINTER(C.c_uint64)]),
     "lv_exchange_flush": (C.c_int, [_vp]),

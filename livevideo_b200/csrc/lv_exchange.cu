@@ -285,6 +285,7 @@ struct lv_exchange {
     cudaStream_t coll = nullptr;           // the collects run here: a collect only reads local memory, so it depends on no
                                            // push of this rank and can already be spinning when the last block arrives
     unsigned long long *h_done = nullptr;  // host-mapped: number of steps whose table is complete (written by the collects)
+    cudaEvent_t ev_collected = nullptr;    // behind the newest collect launch (lv_exchange_wait_table)
     cudaEvent_t *ev_kernel = nullptr;      // [depth] fused kernel of the step in this ring slot has finished
     cudaEvent_t *ev_pushed = nullptr;      // [depth] the push of the step in this ring slot has read its row
     uint32_t *tables = nullptr;            // ring of collected tables: depth x world x slot_words
@@ -380,6 +381,7 @@ void lv_exchange_destroy(lv_exchange *x)
     delete[] x->ev_pushed;
     if (x->side) cudaStreamDestroy(x->side);
     if (x->coll) cudaStreamDestroy(x->coll);
+    if (x->ev_collected) cudaEventDestroy(x->ev_collected);
     cudaFree(x->tables);
     cudaFree(x->own);
     cudaFree(x->local);
@@ -542,6 +544,7 @@ int ensure_step_state(lv_exchange *x)
     X_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     X_CUDA(cudaStreamCreateWithPriority(&x->side, cudaStreamNonBlocking, prio_hi));
     X_CUDA(cudaStreamCreateWithPriority(&x->coll, cudaStreamNonBlocking, prio_hi));
+    X_CUDA(cudaEventCreateWithFlags(&x->ev_collected, cudaEventDisableTiming));
     x->ev_kernel = new (std::nothrow) cudaEvent_t[d]();
     x->ev_pushed = new (std::nothrow) cudaEvent_t[d]();
     if (!x->ev_kernel || !x->ev_pushed) return LV_E_NOMEM;
@@ -560,6 +563,7 @@ int collect_through(lv_exchange *x, uint64_t step)
         k_collect<<<1, 256, 0, x->coll>>>(x->peers, x->L, x->rank, x->collected, (int)(step + 1 - x->collected), nullptr, x->tables,
                                           x->h_err, x->h_done, x->trace);
         X_CUDA(cudaGetLastError());
+        X_CUDA(cudaEventRecord(x->ev_collected, x->coll));
         x->collected = step + 1;
     }
     return LV_OK;
@@ -653,6 +657,21 @@ int lv_exchange_result(lv_exchange *x, uint64_t step, const uint32_t **d_table)
         return LV_E_STATE;
     }
     *d_table = x->tables + (size_t)(step % (uint64_t)x->L.depth) * x->world * x->L.slot_words;
+    return LV_OK;
+}
+
+/* The device-side form of lv_exchange_result: makes `cuda_stream` wait until the table of `step` is complete, without
+ * involving the host (a kernel that consumes the table is simply enqueued behind this call); *d_table as in
+ * lv_exchange_result. */
+int lv_exchange_wait_table(lv_exchange *x, uint64_t step, void *cuda_stream, const uint32_t **d_table)
+{
+    if (!x) return LV_E_ARG;
+    if (!x->stepping || step >= x->steps || x->steps - step > (uint64_t)x->L.depth) return LV_E_STATE;
+    DevGuard g(x->device);
+    int rc = collect_through(x, step);
+    if (rc != LV_OK) return rc;
+    X_CUDA(cudaStreamWaitEvent((cudaStream_t)cuda_stream, x->ev_collected, 0));     // every collect launched so far
+    if (d_table) *d_table = x->tables + (size_t)(step % (uint64_t)x->L.depth) * x->world * x->L.slot_words;
     return LV_OK;
 }
 

@@ -51,6 +51,13 @@ class PendingGather:
     def wait_summary(self, stream=None):
         """Nothing to do: on this path out["summary"] is written in-stream by the fused kernel."""
 
+    def wait_table(self, stream=None):
+        """Device-side wait for the gathered table (the library collective's own stream semantics)."""
+        if self.work is not None:
+            self.work.wait()          # NCCL: makes the current stream wait, the host does not block
+            self.work = None
+        return self.out.reshape(self.world, self.cap, self.n_frames, 2)
+
     def result(self, copy=True):
         import torch
         if self.work is not None:
@@ -218,20 +225,37 @@ class PeerExchange:
         self._capi.check(self._capi.lib().lv_exchange_wait_summary(self._h, step, stream.cuda_stream),
                          "lv_exchange_wait_summary")
 
+    def _view(self, ptr, step):
+        """Tensor view of the ring slot at `ptr` (the table of `step`).  Wrapping device memory costs tens of
+        microseconds, so the views of ALL ring slots are made at the first call."""
+        t = self._views.get(ptr)
+        if t is None:
+            import torch
+
+            from .api import _DevView
+            nbytes = 4 * self.world * self.slot_words
+            base = ptr - (step % self.depth) * nbytes
+            for s in range(self.depth):
+                self._views[base + s * nbytes] = _DevView(base + s * nbytes, nbytes, self.device).tensor().view(
+                    torch.int32).reshape(self.world, self.slot_words)
+            t = self._views[ptr]
+        return t
+
     def result(self, step, copy=True):
         """int32 CUDA tensor [world, slot_words]: the table of `step` (blocks until every block has arrived).
         copy=False returns a view of the exchange's own ring slot, valid until `depth` further steps are issued."""
         p = self._C.c_void_p()
         self._capi.check(self._capi.lib().lv_exchange_result(self._h, step, self._C.byref(p)), "lv_exchange_result")
-        t = self._views.get(p.value)
-        if t is None:       # one tensor view per ring slot, made once (wrapping device memory costs tens of microseconds)
-            import torch
-
-            from .api import _DevView
-            nbytes = 4 * self.world * self.slot_words
-            t = _DevView(p.value, nbytes, self.device).tensor().view(torch.int32).reshape(self.world, self.slot_words)
-            self._views[p.value] = t
+        t = self._view(p.value, step)
         return t.clone() if copy else t
+
+    def wait_table(self, step, stream):
+        """lv_exchange_wait_table: `stream` waits on the device until the table of `step` is complete; returns the view of
+        the ring slot (valid for `depth` further steps) without blocking the host."""
+        p = self._C.c_void_p()
+        self._capi.check(self._capi.lib().lv_exchange_wait_table(self._h, step, stream.cuda_stream, self._C.byref(p)),
+                         "lv_exchange_wait_table")
+        return self._view(p.value, step)
 
 
 class PendingPeerGather:
@@ -252,6 +276,16 @@ class PendingPeerGather:
         import torch
         o = self.owner
         o.exchange.wait_summary(self.step, stream or torch.cuda.current_stream(o.device))
+
+    def wait_table(self, stream=None):
+        """The device-side result(): `stream` (default: the current one) waits until this step's table is complete and the
+        table is returned at once -- its consumer is enqueued behind this call, the host never blocks.  Returns
+        [world, cap, n_frames, 2] (rank-padded) as a view of the exchange's ring slot."""
+        import torch
+        o = self.owner
+        cap = max_shard(o.total_streams, o.world)
+        tab = o.exchange.wait_table(self.step, stream or torch.cuda.current_stream(o.device))
+        return tab[:, : cap * self.n_frames * 2].reshape(o.world, cap, self.n_frames, 2)
 
     def result(self, copy=True):
         """[total_streams, n_frames, 2].  copy=False: when every rank owns the same number of streams the table is

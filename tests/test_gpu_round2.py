@@ -366,6 +366,12 @@ def _ipc_worker(rank, world, port, q):
                 sc.gate(hold=(rank == 0))                     # device-side rendezvous, mid-run (rank 0 holds its arrival)
             hd = sc.step_async(d_in, T, out)
             sc.gate_open()                                    # no-op unless a held gate is pending
+            if k % 4 == 1:
+                # device-side pick-up: the current stream waits for the table, the copy is enqueued behind the wait
+                tab = hd.wait_table().clone()
+                parts = [tab[r, :shard_range(S, world, r)[1]] for r in range(world)]
+                got = torch.cat(parts, dim=0).cpu().numpy().view(np.uint32).reshape(S * T, 2)
+                ok = ok and np.array_equal(got, want)
             if k % 4 == 3 or k == steps - 1:
                 got = hd.result().cpu().numpy().view(np.uint32).reshape(S * T, 2)
                 ok = ok and np.array_equal(got, want)
