@@ -291,8 +291,8 @@ LV_API const uint32_t *lv_shard_gathered(lv_shard *s, int rank);
 LV_API int lv_shard_sync(lv_shard *s);
 
 /* ---- kernel variant (process-wide) -------------------------------------------------------------------
- * 0 = tiled kernel (default), 1 = TMA pipeline (cp.async.bulk.tensor loads/stores), 2 = register-pipelined
- * strips.  All variants are bit-identical; the choice only affects speed (DESIGN.md has the measurements). */
+ * 0 = tiled kernel (default), 1 = TMA pipeline (cp.async.bulk.tensor loads/stores; measured slower, kept as the one
+ * selectable alternative).  Both are bit-identical; the choice only affects speed (DESIGN.md has the measurements). */
 LV_API int lv_set_kernel_variant(int variant);
 LV_API int lv_get_kernel_variant(void);
 

@@ -477,11 +477,11 @@ def host_unregister(a):
     capi.check(capi.lib().lv_host_unregister(a.ctypes.data), "lv_host_unregister")
 
 
-KERNEL_VARIANTS = {"tile": 0, "tma": 1, "strip": 2}
+KERNEL_VARIANTS = {"tile": 0, "tma": 1}
 
 
 def set_kernel_variant(name):
-    """Select the kernel variant ("tile" default, "tma", "strip"); all are bit-identical."""
+    """Select the kernel variant ("tile" default, "tma"); both are bit-identical."""
     capi.check(capi.lib().lv_set_kernel_variant(KERNEL_VARIANTS[name]), "lv_set_kernel_variant")
 
 

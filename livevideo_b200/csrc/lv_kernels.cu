@@ -405,26 +405,23 @@ __global__ void k_diff_generic(int w, int h, const uint8_t *__restrict__ cur, co
 
 }  // namespace
 
-// Kernel variant: 0 = tiled (default, fastest: profiles/), 1 = TMA pipeline, 2 = register-pipelined strips.
-// All three produce identical bytes (tests/test_gpu_parity.py runs the parity suite over each).  The
-// environment variable LV_KERNEL=tile|tma|strip sets the initial value; lv_set_kernel_variant() overrides it.
+// Kernel variant: 0 = tiled (default, fastest: profiles/), 1 = TMA pipeline (the one measured-and-rejected design kept
+// selectable).  Both produce identical bytes (tests/test_gpu_parity.py runs the parity suite over each).  The
+// environment variable LV_KERNEL=tile|tma sets the initial value; lv_set_kernel_variant() overrides it.
 static int g_variant = -1;
 int kernel_variant()
 {
     if (g_variant < 0) {
         const char *e = getenv("LV_KERNEL");
-        g_variant = !e ? 0 : (e[0] == 's' ? 2 : (e[0] == 't' && e[1] == 'm') ? 1 : 0);
+        g_variant = (e && e[0] == 't' && e[1] == 'm') ? 1 : 0;
     }
     return g_variant;
 }
-void set_kernel_variant(int v) { g_variant = v < 0 || v > 2 ? 0 : v; }
+void set_kernel_variant(int v) { g_variant = v == 1 ? 1 : 0; }
 static bool use_tma() { return kernel_variant() == 1; }
-static bool use_strip() { return kernel_variant() == 2; }
 
 int launch_step(const StepArgs &s, cudaStream_t st)
 {
-    if (use_strip() && !s.static_ref && !s.boxes)
-        if (int r = launch_step_strip(s, st)) return r;
     if (use_tma() && !s.static_ref && !s.boxes)
         if (int r = launch_step_tma(s, st)) return r;   // 0 = geometry/alignment not eligible for the TMA pipeline
     KArgs a{};
@@ -475,8 +472,6 @@ int launch_step_init(uint32_t *summary, size_t n_frames, const int *windows, int
 
 int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st)
 {
-    if (use_strip())
-        if (int r = launch_convert_strip(g, i420, n_frames, bgr, st)) return r;
     if (use_tma())
         if (int r = launch_convert_tma(g, i420, n_frames, bgr, st)) return r;
     KArgs a{};
@@ -486,8 +481,6 @@ int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bg
 
 int launch_diff(const DiffArgs &d, cudaStream_t st)
 {
-    if (use_strip())
-        if (int r = launch_diff_strip(d, st)) return r;
     if (use_tma())
         if (int r = launch_diff_tma(d, st)) return r;
     KArgs a{};

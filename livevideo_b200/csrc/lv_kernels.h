@@ -74,12 +74,6 @@ int launch_step_tma(const StepArgs &a, cudaStream_t st);
 int launch_convert_tma(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st);
 int launch_diff_tma(const DiffArgs &a, cudaStream_t st);
 
-// The register-pipelined strip kernel (lv_strip.cu); same return convention.
-bool strip_supported(const Geom &g);
-int launch_step_strip(const StepArgs &a, cudaStream_t st);
-int launch_convert_strip(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st);
-int launch_diff_strip(const DiffArgs &a, cudaStream_t st);
-
 // lv_aux.cu: background subtraction (WriteBks) and object box
 int launch_write_bks(const Geom &g, const uint8_t *cur, const uint8_t *bkd, int n_frames, int tol, uint8_t *out,
                      uint16_t *obj_bits, cudaStream_t st);

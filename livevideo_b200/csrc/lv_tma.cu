@@ -1,4 +1,7 @@
-// lv_tma.cu -- the production kernel: warp-autonomous TMA pipeline for the fused step (sm_100a).
+// lv_tma.cu -- OPT-IN variant (lv_set_kernel_variant(1) / LV_KERNEL=tma), NOT the default: a warp-autonomous TMA pipeline for
+// the fused step (sm_100a).  Bit-identical to the tiled kernel of lv_kernels.cu but measured at about half its speed
+// (148-158 us at 1080p x 64, 532-576 us at 4K x 32: stall_mio on UTMALDG with 1 KB boxes); kept as the one
+// measured-and-rejected design that stays selectable.
 //
 // Every warp is its own producer/consumer pipeline; there is no block-level synchronisation at all.
 //   item   = one macroblock-row segment of 128 pixels x 16 rows of one frame (8 macroblocks)

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np, torch
 import livevideo_b200 as lv, lvoracle as orc
 
-for variant in ("tile", "tma", "strip"):
+for variant in ("tile", "tma"):
     lv.set_kernel_variant(variant)
     for (w, h, ns, nf) in [(352, 288, 2, 2), (96, 20, 1, 2), (1920, 1080, 1, 2)]:
         frames = orc.gen_batch("camera", 1, ns, nf, w, h)
