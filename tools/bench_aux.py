@@ -50,6 +50,18 @@ def main():
     print(f"# {w}x{h} x {n} frames, peak {peak} GB/s")
     row("fused convert+diff (K1)", timeit(lambda: ctx.convert_diff_batch(d_in, 1, n, lean)), 5.5)
     row("fused + bit mask", timeit(lambda: ctx.convert_diff_batch(d_in, 1, n, {**lean, "mask_bits": out["mask_bits"]})), 5.625)
+    # the fused step with the object boxes accumulated by the same launch (lv_convert_diff_box_batch): windows of the
+    # reference's size (an object of 96 x 64 px + 8 px margin) and the whole picture
+    for tag, n_obj, whole in (("1 object window", 1, False), ("4 object windows", 4, False), ("whole picture", 1, True)):
+        wins = torch.empty((n, n_obj, 4), dtype=torch.int32)
+        for f in range(n):
+            for k in range(n_obj):
+                x0, y0 = (97 * f + 411 * k) % max(1, w - 112), (53 * f + 177 * k) % max(1, h - 80)
+                wins[f, k] = torch.tensor([0, w - 1, 0, h - 1] if whole else [x0, x0 + 111, y0, y0 + 79])
+        d_w = wins.cuda()
+        boxes = torch.empty((n, n_obj, 4), dtype=torch.int32, device="cuda")
+        row(f"fused + object box ({tag})", timeit(lambda: ctx.convert_diff_box_batch(d_in, 1, n, lean, d_w, boxes)), 5.5,
+            note="no mask in memory; init kernel in place of the summary memset")
     row("convert only (K2)", timeit(lambda: ctx.convert_batch(d_in, n, out["bgr"])), 4.5)
     # difference only over explicit planes: cur = luma planes of the batch, ref = the same shifted by one frame
     ys = torch.stack([d_in[f * ctx.frame_bytes: f * ctx.frame_bytes + px] for f in range(n)]).reshape(-1).contiguous()
