@@ -296,6 +296,18 @@ LV_API int lv_shard_sync(lv_shard *s);
 LV_API int lv_set_kernel_variant(int variant);
 LV_API int lv_get_kernel_variant(void);
 
+/* ---- zero-copy mode of the host-pointer conversion entries (process-wide) ------------------------------
+ * Buffers handed out by lv_host_alloc or pinned in place by lv_host_register are also MAPPED into the device's address
+ * space.  When every buffer of a YV12_to_RGB24 / lv_convert_host_multi / FrameDiff_MB call is such a buffer (planes and
+ * picture 16-byte aligned, chroma planes 8-byte), the kernel reads the planes from host memory and writes the result to
+ * host memory itself: one launch + one synchronise per call, upload and download of the same picture overlapped on the
+ * link.  0 = off (always stage through device buffers), 1 = on with the tile kernel's store pattern, 2 = on with stores
+ * re-dealt to 512 contiguous bytes per warp instruction (default; environment variable LV_ZEROCOPY sets the initial
+ * value).  Results are identical in every mode.  Replaces nothing in the reference's interface: the calls stay
+ * Convert.h:26 / MainDlg.cpp:946-974 as they are. */
+LV_API int lv_set_zero_copy(int mode);
+LV_API int lv_get_zero_copy(void);
+
 /* ---- introspection for the benchmark ------------------------------------------------------------- */
 LV_API uint64_t lv_kernel_launches(const lv_ctx *ctx);   /* kernels of this library launched so far */
 LV_API int lv_device_sm_count(const lv_ctx *ctx);

@@ -7,7 +7,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "liblivevideo.so")
-SOURCES = ["lv_kernels.cu", "lv_tma.cu", "lv_aux.cu", "lv_formats.cu", "lv_shard.cu", "lv_exchange.cu", "lv_capi.cu", "lv_synth.cu"]
+SOURCES = ["lv_kernels.cu", "lv_zerocopy.cu", "lv_tma.cu", "lv_aux.cu", "lv_formats.cu", "lv_shard.cu", "lv_exchange.cu", "lv_capi.cu", "lv_synth.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -490,6 +490,21 @@ def get_kernel_variant():
     return {n: k for k, n in KERNEL_VARIANTS.items()}[v]
 
 
+ZERO_COPY_MODES = {"off": 0, "plain": 1, "staged": 2}
+
+
+def set_zero_copy(name):
+    """Zero-copy mode of the host-pointer conversion entries on buffers pinned through this library: "off" (always stage
+    through device buffers), "plain" (tile kernel's store pattern) or "staged" (default: 512 contiguous bytes per warp
+    store).  Results are identical in every mode."""
+    capi.check(capi.lib().lv_set_zero_copy(ZERO_COPY_MODES[name]), "lv_set_zero_copy")
+
+
+def get_zero_copy():
+    v = capi.lib().lv_get_zero_copy()
+    return {n: k for k, n in ZERO_COPY_MODES.items()}[v]
+
+
 def gen_synthetic(kind, seed, first_stream, first_frame, n_streams, n_frames, width, height, out=None, device=0,
                   cuda_stream=None):
     """Synthetic I420 frames on the device (`uniform` or `camera` generator)."""

@@ -92,6 +92,8 @@ SYMBOLS = {
     "lv_exchange_last_error": (C.c_char_p, []),
     "lv_set_kernel_variant": (C.c_int, [C.c_int]),
     "lv_get_kernel_variant": (C.c_int, []),
+    "lv_set_zero_copy": (C.c_int, [C.c_int]),
+    "lv_get_zero_copy": (C.c_int, []),
     "lv_kernel_launches": (C.c_uint64, [_vp]),
     "lv_device_sm_count": (C.c_int, [_vp]),
     "lv_gen_synthetic": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -10,7 +10,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #ifndef LV_HOST_CHUNK_MB_DEFAULT
 #define LV_HOST_CHUNK_MB_DEFAULT 16
@@ -97,6 +99,60 @@ int misaligned(const char *what)
 {
     snprintf(g_err, sizeof g_err, "%s is not aligned as include/livevideo.h requires", what);
     return LV_E_ARG;
+}
+
+// ---- host ranges pinned AND mapped through this library (lv_host_alloc / lv_host_register) -----------------------------
+// The legacy entries look their pointers up here (no CUDA call on the way): a hit means the kernel may address the
+// range directly.  dev - host is the constant offset of the mapping (0 on every UVA platform we have seen).
+struct PinnedRange {
+    uintptr_t base;
+    size_t bytes;
+    intptr_t dev_off;
+};
+std::mutex g_pinned_mu;
+std::vector<PinnedRange> g_pinned;
+
+void pinned_add(void *p, size_t bytes)
+{
+    void *d = nullptr;
+    if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess || !d) {
+        cudaGetLastError();        // not mappable here: the range is still pinned, the staged path serves it
+        return;
+    }
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned.push_back({reinterpret_cast<uintptr_t>(p), bytes, (intptr_t)(reinterpret_cast<uintptr_t>(d) - reinterpret_cast<uintptr_t>(p))});
+}
+
+void pinned_remove(void *p)
+{
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    for (size_t i = 0; i < g_pinned.size(); i++)
+        if (g_pinned[i].base == reinterpret_cast<uintptr_t>(p)) {
+            g_pinned.erase(g_pinned.begin() + (long)i);
+            return;
+        }
+}
+
+// device address of host bytes [p, p + n) when the whole span lies in one mapped range, else NULL
+uint8_t *mapped(const void *p, size_t n)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    for (const PinnedRange &r : g_pinned)
+        if (a >= r.base && a + n <= r.base + r.bytes) return reinterpret_cast<uint8_t *>(a + r.dev_off);
+    return nullptr;
+}
+
+// 0 = never address host memory from a kernel (always stage through device buffers), 1 = zero-copy with the tile
+// kernel's store pattern, 2 = zero-copy with link-friendly stores (default).  LV_ZEROCOPY sets the initial value.
+int g_zero_copy = -1;
+int zero_copy_mode()
+{
+    if (g_zero_copy < 0) {
+        const char *e = getenv("LV_ZEROCOPY");
+        g_zero_copy = (e && e[0] >= '0' && e[0] <= '2' && !e[1]) ? e[0] - '0' : 2;
+    }
+    return g_zero_copy;
 }
 
 void free_pipeline(lv_ctx *c)
@@ -559,33 +615,48 @@ int lv_host_alloc(void **p, size_t bytes)
 {
     if (!p) return LV_E_ARG;
     *p = nullptr;
-    LV_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+    LV_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
+    pinned_add(*p, bytes ? bytes : 1);
     return LV_OK;
 }
 
 int lv_host_free(void *p)
 {
     if (!p) return LV_OK;
+    pinned_remove(p);
     LV_CUDA(cudaFreeHost(p));
     return LV_OK;
 }
 
 // Pin memory the application already owns (the reference's dialogs malloc their planes and the RGB buffer once,
 // MainDlg.cpp:39-51, and reuse them for every picture): the legacy entries and lv_step_host then DMA straight from / to
-// it instead of going through the driver's pageable staging.  The range must stay allocated until lv_host_unregister.
+// it instead of going through the driver's pageable staging, and -- the range is also MAPPED into the device's address
+// space -- the conversion entries read and write it directly from the kernel (lv_zerocopy.cu).  The range must stay
+// allocated until lv_host_unregister.
 int lv_host_register(void *p, size_t bytes)
 {
     if (!p || !bytes) return LV_E_ARG;
-    LV_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    LV_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    pinned_add(p, bytes);
     return LV_OK;
 }
 
 int lv_host_unregister(void *p)
 {
     if (!p) return LV_OK;
+    pinned_remove(p);
     LV_CUDA(cudaHostUnregister(p));
     return LV_OK;
 }
+
+int lv_set_zero_copy(int mode)
+{
+    if (mode < 0 || mode > 2) return LV_E_ARG;
+    g_zero_copy = mode;
+    return LV_OK;
+}
+
+int lv_get_zero_copy(void) { return zero_copy_mode(); }
 
 // Host step.  The batch is cut along the frame axis into chunks (all streams, a few frames each):
 // chunk k's previous luma is chunk k-1's last frame, which is exactly what the carried state holds
@@ -826,6 +897,19 @@ void YV12_to_RGB24(unsigned char *src0, unsigned char *src1, unsigned char *src2
     LegacyScope scope(fn);
     cudaStream_t st = scope.st;
     const size_t px = (size_t)width * height;
+    if (zero_copy_mode() && geom_fast(width, height)) {
+        // all four buffers pinned + mapped in place: one kernel reads the planes and writes the picture over the link
+        lv::PlaneTable t{};
+        t.y[0] = mapped(src0, px); t.u[0] = mapped(src1, px / 4); t.v[0] = mapped(src2, px / 4); t.dst[0] = mapped(dst_ori, 3 * px);
+        if (t.y[0] && t.u[0] && t.v[0] && t.dst[0] && aligned(t.y[0], 16) && aligned(t.dst[0], 16) && aligned(t.u[0], 8) &&
+            aligned(t.v[0], 8)) {
+            const int r = lv::launch_convert_planes(lv::make_geom(width, height), t, 1, zero_copy_mode() == 2, st);
+            if (r < 0) { cuda_fail((cudaError_t)(-r), "launch"); legacy_die(fn, "kernel launch failed"); }
+            const cudaError_t ez = cudaStreamSynchronize(st);
+            if (ez != cudaSuccess) { cuda_fail(ez, "zero-copy kernel"); legacy_die(fn, "kernel failed"); }
+            return;
+        }
+    }
     uint8_t *din = t_in.get(px + px / 2), *dout = t_out.get(3 * px);
     if (!din || !dout) legacy_die(fn, "device allocation failed");
     cudaError_t e = cudaMemcpyAsync(din, src0, px, cudaMemcpyHostToDevice, st);
@@ -883,6 +967,32 @@ void FrameDiff_MB(const unsigned char *cur_y, const unsigned char *ref_y, int wi
     const size_t px = (size_t)width * height;
     const int mb_w = (width + 15) / 16, mb_h = (height + 15) / 16;
     const size_t mbs = (size_t)mb_w * mb_h;
+    if (zero_copy_mode() && geom_fast(width, height) && tol >= 0 && lv::kernel_variant() == 0) {
+        // the planes (and the byte mask) pinned + mapped in place: the difference kernel addresses them directly; the two
+        // small per-macroblock outputs go the same way when they are mapped too, else through the device scratch
+        lv::DiffArgs a{};
+        a.g = lv::make_geom(width, height); a.n_frames = 1; a.tol = tol; a.mb_thresh = mb_thresh;
+        a.cur_y = mapped(cur_y, px); a.ref_y = mapped(ref_y, px);
+        a.mask_bytes = mask ? mapped(mask, px) : nullptr;
+        if (a.cur_y && a.ref_y && aligned(a.cur_y, 16) && aligned(a.ref_y, 16) && (!mask || (a.mask_bytes && aligned(a.mask_bytes, 16)))) {
+            uint16_t *zc_cnt = mb_count ? reinterpret_cast<uint16_t *>(mapped(mb_count, 2 * mbs)) : nullptr;
+            uint8_t *zc_map = mb_map ? mapped(mb_map, mbs) : nullptr;
+            if (zc_cnt && !aligned(zc_cnt, 2)) zc_cnt = nullptr;
+            const size_t cnt_bytes = (2 * mbs + 15) & ~(size_t)15;
+            uint8_t *scratch = ((mb_count && !zc_cnt) || (mb_map && !zc_map)) ? t_out.get(cnt_bytes + mbs) : nullptr;
+            if (((mb_count && !zc_cnt) || (mb_map && !zc_map)) && !scratch) legacy_die(fn, "device allocation failed");
+            a.mb_count = mb_count ? (zc_cnt ? zc_cnt : reinterpret_cast<uint16_t *>(scratch)) : nullptr;
+            a.mb_map = mb_map ? (zc_map ? zc_map : scratch + cnt_bytes) : nullptr;
+            const int r = lv::launch_diff(a, st);
+            if (r < 0) { cuda_fail((cudaError_t)(-r), "launch"); legacy_die(fn, "kernel launch failed"); }
+            cudaError_t ez = cudaSuccess;
+            if (mb_count && !zc_cnt) ez = cudaMemcpyAsync(mb_count, scratch, 2 * mbs, cudaMemcpyDeviceToHost, st);
+            if (mb_map && !zc_map && ez == cudaSuccess) ez = cudaMemcpyAsync(mb_map, scratch + cnt_bytes, mbs, cudaMemcpyDeviceToHost, st);
+            if (ez == cudaSuccess) ez = cudaStreamSynchronize(st);
+            if (ez != cudaSuccess) { cuda_fail(ez, "zero-copy kernel"); legacy_die(fn, "kernel failed"); }
+            return;
+        }
+    }
     // layout of the output scratch: mask bytes | counts (u16, 2-byte aligned) | map
     const size_t off_cnt = (px + 15) & ~(size_t)15, off_map = off_cnt + ((2 * mbs + 15) & ~(size_t)15);
     uint8_t *din = t_in.get(2 * ((px + 15) & ~(size_t)15)), *dout = t_out.get(off_map + mbs);
@@ -998,6 +1108,28 @@ int lv_convert_host_multi(const unsigned char *const *src0, const unsigned char 
     const size_t px = (size_t)width * height;
     const bool fast = geom_fast(width, height);
     const lv::Geom g = lv::make_geom(width, height);
+    if (zero_copy_mode() && fast) {
+        // every picture's four buffers pinned + mapped in place: up to 8 pictures per launch straight over the link
+        bool all = true;
+        for (int i = 0; i < n && all; i++) {
+            const uint8_t *y = mapped(src0[i], px), *u = mapped(src1[i], px / 4), *v = mapped(src2[i], px / 4), *d = mapped(dst_ori[i], 3 * px);
+            all = y && u && v && d && aligned(y, 16) && aligned(d, 16) && aligned(u, 8) && aligned(v, 8);
+        }
+        if (all) {
+            for (int i0 = 0; i0 < n; i0 += lv::PlaneTable::kMax) {
+                const int m = n - i0 < lv::PlaneTable::kMax ? n - i0 : lv::PlaneTable::kMax;
+                lv::PlaneTable t{};
+                for (int j = 0; j < m; j++) {
+                    t.y[j] = mapped(src0[i0 + j], px); t.u[j] = mapped(src1[i0 + j], px / 4); t.v[j] = mapped(src2[i0 + j], px / 4);
+                    t.dst[j] = mapped(dst_ori[i0 + j], 3 * px);
+                }
+                const int r = lv::launch_convert_planes(g, t, m, zero_copy_mode() == 2, P.s_k);
+                if (r < 0) return P.drain(cuda_fail((cudaError_t)(-r), "kernel launch"));
+            }
+            LV_MP(cudaStreamSynchronize(P.s_k));
+            return LV_OK;
+        }
+    }
     for (int i = 0; i < n; i++) {
         const int slot = i % MultiPipe::kSlots;
         uint8_t *din = P.in[slot].get(px + px / 2), *dout = P.out[slot].get(3 * px);

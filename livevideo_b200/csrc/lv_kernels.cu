@@ -233,59 +233,71 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
         }
     }
 
-    if constexpr (kBox) {
-        // Per object: clip the thread's mask rows to the window, reduce min / max over the warp (REDUX), park the warp's
-        // result; the first warp finishes the block behind the barrier below.  A block whose rectangle misses the window
-        // (block-uniform test) skips the object.
-        __shared__ int sbox[kMaxObjects][8][4];
-        const int xs = unit * 16;
-        for (int k = 0; k < a.n_obj; k++) {
-            const int4 wd = __ldg(a.windows + (size_t)f * a.n_obj + k);      // x0, x1, y0, y1
-            int lo = wd.x - xs, hi = wd.y - xs;
-            lo = lo < 0 ? 0 : lo;
-            hi = hi > 15 ? 15 : hi;
-            const uint32_t cm = (active && lo <= hi) ? ((2u << hi) - (1u << lo)) : 0u;
-            const uint32_t r0 = (row0 >= wd.z && row0 <= wd.w) ? bm0 & cm : 0u;
-            const uint32_t r1 = (row0 + 1 >= wd.z && row0 + 1 <= wd.w) ? bm1 & cm : 0u;
-            const uint32_t any = r0 | r1;
-            int mnx = 0x7fffffff, mxx = -0x7fffffff, mny = 0x7fffffff, mxy = -0x7fffffff;
-            if (any) {
-                mnx = xs + __ffs((int)any) - 1;
-                mxx = xs + 31 - __clz((int)any);
-                mny = r0 ? row0 : row0 + 1;
-                mxy = r1 ? row0 + 1 : row0;
-            }
-            mnx = __reduce_min_sync(0xffffffffu, mnx);
-            mxx = __reduce_max_sync(0xffffffffu, mxx);
-            mny = __reduce_min_sync(0xffffffffu, mny);
-            mxy = __reduce_max_sync(0xffffffffu, mxy);
-            if (tx == 0) {
-                sbox[k][ty][0] = mnx; sbox[k][ty][1] = mxx; sbox[k][ty][2] = mny; sbox[k][ty][3] = mxy;
-            }
-        }
-        __syncthreads();
-        if (ty == 0) {
-            for (int j = tx; j < 4 * a.n_obj; j += 32) {
-                const int k = j >> 2, c = j & 3;
-                int v = sbox[k][0][c];
-#pragma unroll
-                for (int i = 1; i < 8; i++) v = (c & 1) ? max(v, sbox[k][i][c]) : min(v, sbox[k][i][c]);
-                int *dst = reinterpret_cast<int *>(a.boxes + (size_t)f * a.n_obj + k) + c;
-                // a changed pixel was seen (v is not the neutral value) and it improves what is there: one atomic
-                if (c & 1) {
-                    if (v != -0x7fffffff && v > *reinterpret_cast<volatile int *>(dst)) atomicMax(dst, v);
-                } else {
-                    if (v != 0x7fffffff && v < *reinterpret_cast<volatile int *>(dst)) atomicMin(dst, v);
-                }
-            }
-        }
-    }
+    // kBox: every thread parks its two 16-pixel mask rows (one word); behind the barrier of the macroblock reduction the
+    // block's SECOND warp owns the boxes: lane tx holds the 16 x 16 mask of the block's macroblock tx in 8 registers, clips
+    // it to each object's window with two bit masks (columns, rows), and the warp reduces min / max once per object
+    // (REDUX) -- per object the other seven warps do nothing at all.
+    __shared__ uint32_t smask[kBox ? 8 : 1][32];
+    if constexpr (kBox) smask[ty][tx] = bm0 | (bm1 << 16);
 
     if constexpr (kDiff) {
         // 8 row-pair partial counts per macroblock -> shared memory -> the first warp finishes the block
         __shared__ uint32_t part[8][32];
         part[ty][tx] = cnt;
         __syncthreads();
+        if constexpr (kBox) {
+            if (ty == 1) {
+                uint32_t mw[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) mw[i] = smask[i][tx];
+                const int xs = unit * 16, yb = mby * 16;
+                const bool mine = unit < g.units;            // lanes past the last macroblock of the picture hold zeros anyway
+                for (int k = 0; k < a.n_obj; k++) {
+                    const int4 wd = __ldg(a.windows + (size_t)f * a.n_obj + k);      // x0, x1, y0, y1 (inclusive)
+                    int lo = wd.x - xs, hi = wd.y - xs, rlo = wd.z - yb, rhi = wd.w - yb;
+                    lo = lo < 0 ? 0 : lo;
+                    hi = hi > 15 ? 15 : hi;
+                    rlo = rlo < 0 ? 0 : rlo;
+                    rhi = rhi > 15 ? 15 : rhi;
+                    const uint32_t cm = (mine && lo <= hi) ? ((2u << hi) - (1u << lo)) : 0u;
+                    const uint32_t rm = rlo <= rhi ? ((2u << rhi) - (1u << rlo)) : 0u;
+                    if (!__any_sync(0xffffffffu, cm != 0u && rm != 0u)) continue;      // the block misses the window
+                    const uint32_t cm2 = cm * 0x00010001u;
+                    uint32_t accx = 0u, rows = 0u;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        // rows 2i (low halfword) and 2i+1 (high halfword) of the macroblock
+                        const uint32_t sel = ((rm >> (2 * i)) & 1u ? 0x0000ffffu : 0u) | ((rm >> (2 * i + 1)) & 1u ? 0xffff0000u : 0u);
+                        const uint32_t v = mw[i] & cm2 & sel;
+                        accx |= v;
+                        rows |= (v & 0xffffu ? 1u << (2 * i) : 0u) | (v >> 16 ? 2u << (2 * i) : 0u);
+                    }
+                    const uint32_t anyx = (accx | (accx >> 16)) & 0xffffu;
+                    if (!__any_sync(0xffffffffu, anyx != 0u)) continue;                 // nothing changed inside it
+                    int mnx = 0x7fffffff, mxx = -0x7fffffff, mny = 0x7fffffff, mxy = -0x7fffffff;
+                    if (anyx) {
+                        mnx = xs + __ffs((int)anyx) - 1;
+                        mxx = xs + 31 - __clz((int)anyx);
+                        mny = yb + __ffs((int)rows) - 1;
+                        mxy = yb + 31 - __clz((int)rows);
+                    }
+                    mnx = __reduce_min_sync(0xffffffffu, mnx);
+                    mxx = __reduce_max_sync(0xffffffffu, mxx);
+                    mny = __reduce_min_sync(0xffffffffu, mny);
+                    mxy = __reduce_max_sync(0xffffffffu, mxy);
+                    // it improves what is there: one atomic (lanes 0..3 take one bound each)
+                    if (tx < 4) {
+                        int *dst = reinterpret_cast<int *>(a.boxes + (size_t)f * a.n_obj + k) + tx;
+                        const int v = tx == 0 ? mnx : tx == 1 ? mxx : tx == 2 ? mny : mxy;
+                        if (tx & 1) {
+                            if (v > *reinterpret_cast<volatile int *>(dst)) atomicMax(dst, v);
+                        } else {
+                            if (v < *reinterpret_cast<volatile int *>(dst)) atomicMin(dst, v);
+                        }
+                    }
+                }
+            }
+        }
         if (ty == 0) {
             uint32_t tot = 0;
 #pragma unroll

@@ -64,6 +64,15 @@ int launch_step_init(uint32_t *summary, size_t n_frames, const int *windows, int
 int launch_convert(const Geom &g, const uint8_t *i420, int n_frames, uint8_t *bgr, cudaStream_t st);
 int launch_diff(const DiffArgs &a, cudaStream_t st);
 
+// lv_zerocopy.cu: conversion of up to 8 pictures whose planes are separate allocations the device can address directly
+// (host memory pinned and mapped in place): y/dst 16-byte aligned, u/v 8-byte aligned.
+struct PlaneTable {
+    static const int kMax = 8;
+    const uint8_t *y[kMax], *u[kMax], *v[kMax];
+    uint8_t *dst[kMax];
+};
+int launch_convert_planes(const Geom &g, const PlaneTable &t, int n, bool staged_stores, cudaStream_t st);
+
 int kernel_variant();
 void set_kernel_variant(int v);
 

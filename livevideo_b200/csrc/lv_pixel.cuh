@@ -129,16 +129,17 @@ __device__ __forceinline__ uint32_t diff_gt4(uint32_t a, uint32_t b, uint32_t to
     return r;
 }
 
-// 16 pixels -> 16-bit mask, bit i = pixel i changed
+// 16 pixels -> 16-bit mask, bit i = pixel i changed.  The gather of the four compare bits of a word is one IDP.4A
+// against the byte weights 1,2,4,8 (second word: 16..128), exactly the instruction the counting path spends per word
+// (diff_count16), so the mask costs what the count costs: 128 * byte per word pair, two pairs joined by one IMAD + SHF.
 __device__ __forceinline__ uint32_t diff_mask16(const uint4 &cur, const uint4 &ref, uint32_t tol4,
                                                 uint32_t ntol7)
 {
-    // gather bit 7 of each byte into a nibble: (x & 0x80808080) * 0x00204081 >> 28
-    const uint32_t g0 = (diff_gt4(cur.x, ref.x, tol4, ntol7) & 0x80808080u) * 0x00204081u >> 28;
-    const uint32_t g1 = (diff_gt4(cur.y, ref.y, tol4, ntol7) & 0x80808080u) * 0x00204081u >> 28;
-    const uint32_t g2 = (diff_gt4(cur.z, ref.z, tol4, ntol7) & 0x80808080u) * 0x00204081u >> 28;
-    const uint32_t g3 = (diff_gt4(cur.w, ref.w, tol4, ntol7) & 0x80808080u) * 0x00204081u >> 28;
-    return g0 | (g1 << 4) | (g2 << 8) | (g3 << 12);
+    uint32_t lo = __dp4a(diff_gt4(cur.x, ref.x, tol4, ntol7) & 0x80808080u, 0x08040201u, 0u);
+    lo = __dp4a(diff_gt4(cur.y, ref.y, tol4, ntol7) & 0x80808080u, 0x80402010u, lo);
+    uint32_t hi = __dp4a(diff_gt4(cur.z, ref.z, tol4, ntol7) & 0x80808080u, 0x08040201u, 0u);
+    hi = __dp4a(diff_gt4(cur.w, ref.w, tol4, ntol7) & 0x80808080u, 0x80402010u, hi);
+    return (hi * 256u + lo) >> 7;
 }
 
 // 16 pixels -> acc + 128 * (number of changed pixels): bit 7 of each byte summed by one IDP.4A per word

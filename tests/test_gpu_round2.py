@@ -184,6 +184,67 @@ def test_diff_host_multi_chained_and_explicit_references(lv, orc, torch_cuda):
         assert np.array_equal(cnt_only[i], cnt[i])
 
 
+# ---- zero-copy: the conversion entries on buffers pinned + mapped in place --------------------------------------------
+@pytest.mark.parametrize("w,h", [(1920, 1080), (1280, 720), (352, 288), (16, 2), (528, 34)])
+def test_zero_copy_entries_match_oracle_in_every_mode(lv, orc, torch_cuda, w, h):
+    """YV12_to_RGB24, its five-picture form (MainDlg.cpp:946-974; 9 pictures = two launches) and FrameDiff_MB on buffers
+    pinned in place: the kernel addresses host memory directly (lv_zerocopy.cu).  Same bytes with zero copy off, with the
+    tile kernel's stores and with the re-dealt stores; a buffer that is NOT pinned, or a misaligned plane, silently takes
+    the staged path."""
+    px = w * h
+    n = 9
+    frames = orc.gen_batch("uniform", 33, n, 1, w, h).reshape(n, -1)
+    ys, us, vs, ds = [], [], [], []
+    for i in range(n):
+        y, u, v, d = _own(px), _own(max(px // 4, 1)), _own(max(px // 4, 1)), _own(3 * px)
+        y[:], u[:px // 4], v[:px // 4] = frames[i, :px], frames[i, px:px + px // 4], frames[i, px + px // 4:]
+        ys.append(y), us.append(u), vs.append(v), ds.append(d)
+    mask, cnt, mp = _own(px), np.frombuffer(mmap.mmap(-1, 2 * 4096 * 4), dtype=np.uint16), _own(4096 * 4)
+    mbs = ((w + 15) // 16) * ((h + 15) // 16)
+    bufs = ys + us + vs + ds + [mask, cnt, mp]
+    for a in bufs:
+        lv.host_register(a)
+    want = [orc.convert_frame(frames[i], w, h) for i in range(n)]
+    wm, wc, wb, _ = orc.frame_diff_mb(ys[1], ys[0], w, h, 20, 0)
+    csc = lv.ColorSpaceConversions()
+    before = lv.get_zero_copy()
+    try:
+        for mode in ("off", "plain", "staged"):
+            lv.set_zero_copy(mode)
+            assert lv.get_zero_copy() == mode
+            for d in ds:
+                d[:] = 0
+            csc.YV12_to_RGB24(ys[0], us[0][:px // 4], vs[0][:px // 4], ds[0], w, h)
+            assert np.array_equal(ds[0], want[0]), mode
+            ds[0][:] = 0
+            csc.YV12_to_RGB24_multi(ys, [u[:px // 4] for u in us], [v[:px // 4] for v in vs], ds, w, h)
+            for i in range(n):
+                assert np.array_equal(ds[i], want[i]), (mode, i)
+            mask[:] = 7
+            cnt[:] = 7
+            mp[:] = 7
+            lv.FrameDiff_MB(ys[1], ys[0], w, h, 20, 0, mask=mask, mb_count=cnt[:mbs], mb_map=mp[:mbs])
+            assert np.array_equal(mask, wm) and np.array_equal(cnt[:mbs], wc) and np.array_equal(mp[:mbs], wb), mode
+            assert cnt[mbs] == 7 and mp[mbs] == 7                      # nothing written past the outputs
+        # one pageable destination / one plane at an odd offset: the staged path serves the call, same bytes
+        lv.set_zero_copy("staged")
+        pageable = np.zeros(3 * px, np.uint8)
+        csc.YV12_to_RGB24(ys[2], us[2][:px // 4], vs[2][:px // 4], pageable, w, h)
+        assert np.array_equal(pageable, want[2])
+        if px > 64:
+            odd = _own(px + 64)
+            lv.host_register(odd)
+            odd[4:4 + px] = ys[3]
+            ds[3][:] = 0
+            csc.YV12_to_RGB24(odd[4:4 + px], us[3][:px // 4], vs[3][:px // 4], ds[3], w, h)
+            assert np.array_equal(ds[3], want[3])
+            lv.host_unregister(odd)
+    finally:
+        lv.set_zero_copy(before)
+        for a in bufs:
+            lv.host_unregister(a)
+
+
 # ---- per-stream state -------------------------------------------------------------------------------------------------
 def test_partial_stream_steps_touch_no_other_state(lv, orc, torch_cuda):
     """Streams stepped in arbitrary sub-ranges and orders keep independent previous-luma state (image.c:1553-1561 per
