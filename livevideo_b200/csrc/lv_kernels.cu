@@ -170,6 +170,13 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
 
     uint32_t cnt = 0;
     [[maybe_unused]] uint32_t bm0 = 0, bm1 = 0;      // kBox: the thread's two 16-pixel mask rows
+    // kBox: lane k of the block's second warp fetches object k's window NOW, with the block's first loads, so that the
+    // box work behind the barrier starts from registers (a dependent global load there would keep the whole block's
+    // registers and shared memory allocated for another memory latency with one warp alive)
+    [[maybe_unused]] int4 wpre = make_int4(0, -1, 0, -1);
+    if constexpr (kBox) {
+        if (ty == 1 && tx < a.n_obj) wpre = __ldg(a.windows + (size_t)f * a.n_obj + tx);
+    }
     if (active) {
         const uint8_t *yf = a.y0 + (size_t)f * a.y_stride;
         const uint32_t off = (uint32_t)row0 * (uint32_t)w + (uint32_t)unit * 16u;
@@ -253,7 +260,9 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
                 const int xs = unit * 16, yb = mby * 16;
                 const bool mine = unit < g.units;            // lanes past the last macroblock of the picture hold zeros anyway
                 for (int k = 0; k < a.n_obj; k++) {
-                    const int4 wd = __ldg(a.windows + (size_t)f * a.n_obj + k);      // x0, x1, y0, y1 (inclusive)
+                    // x0, x1, y0, y1 (inclusive) of object k, from lane k's registers
+                    const int4 wd = make_int4(__shfl_sync(0xffffffffu, wpre.x, k), __shfl_sync(0xffffffffu, wpre.y, k),
+                                              __shfl_sync(0xffffffffu, wpre.z, k), __shfl_sync(0xffffffffu, wpre.w, k));
                     int lo = wd.x - xs, hi = wd.y - xs, rlo = wd.z - yb, rhi = wd.w - yb;
                     lo = lo < 0 ? 0 : lo;
                     hi = hi > 15 ? 15 : hi;
@@ -285,15 +294,13 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
                     mxx = __reduce_max_sync(0xffffffffu, mxx);
                     mny = __reduce_min_sync(0xffffffffu, mny);
                     mxy = __reduce_max_sync(0xffffffffu, mxy);
-                    // it improves what is there: one atomic (lanes 0..3 take one bound each)
+                    // lanes 0..3 take one bound each: fire-and-forget RED.MIN / RED.MAX (reading the bound first to skip
+                    // the atomic would put a dependent global load at the very end of the block's life)
                     if (tx < 4) {
                         int *dst = reinterpret_cast<int *>(a.boxes + (size_t)f * a.n_obj + k) + tx;
                         const int v = tx == 0 ? mnx : tx == 1 ? mxx : tx == 2 ? mny : mxy;
-                        if (tx & 1) {
-                            if (v > *reinterpret_cast<volatile int *>(dst)) atomicMax(dst, v);
-                        } else {
-                            if (v < *reinterpret_cast<volatile int *>(dst)) atomicMin(dst, v);
-                        }
+                        if (tx & 1) atomicMax(dst, v);
+                        else atomicMin(dst, v);
                     }
                 }
             }
