@@ -221,6 +221,18 @@ LV_API int lv_object_box_batch(lv_ctx *ctx, const void *d_mask, int mask_is_bits
 LV_API int lv_narrow_pictures(lv_ctx *ctx, const uint16_t *d_pic16, int n_frames, int size_x, int size_y,
                               int crop_left, int crop_top, uint8_t *d_i420, void *cuda_stream);
 
+/* The same pictures straight into the fused step: lv_narrow_pictures + lv_convert_diff_batch in ONE kernel (the low byte of
+ * every sample is taken and the crop cut away while the pictures are read, so the I420 frames never exist in memory:
+ * 3 B/px in + 3 B/px out instead of 4.5 + 4.5; frame t > 0 is differenced against the previous PICTURE's luma).  d_pic16 =
+ * n_streams * n_frames pictures, stream-major, in the lv_narrow_pictures layout; outputs, state and results exactly as
+ * lv_convert_diff_batch (d_bgr is mandatory here).  The one-kernel path needs d_pic16 16-byte aligned, size_x % 16 == 0,
+ * crop_left % 16 == 0 and plane sizes that are multiples of 8 samples (true for every macroblock-aligned picture); any
+ * other legal layout is served by the two kernels through a scratch the context owns. */
+LV_API int lv_convert_diff_pictures(lv_ctx *ctx, const uint16_t *d_pic16, int size_x, int size_y, int crop_left, int crop_top,
+                                    int first_stream, int n_streams, int n_frames, uint8_t *d_bgr, uint16_t *d_mask_bits,
+                                    uint8_t *d_mask_bytes, uint16_t *d_mb_count, uint8_t *d_mb_map, uint32_t *d_summary,
+                                    void *cuda_stream);
+
 /* Device-pointer form of the five converters above: kind 1 RGB24_to_YV12, 2 YVU9_to_YV12, 3 YUY2_to_YV12,
  * 4 YV12_to_YVU9, 5 YV12_to_YUY2; n_frames frames back to back (bytes per frame: lv_format_bytes). */
 LV_API int lv_convert_format(lv_ctx *ctx, int kind, const uint8_t *d_in, uint8_t *d_out, int n_frames, void *cuda_stream);

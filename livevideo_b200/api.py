@@ -367,6 +367,25 @@ class Context:
             crop_left, crop_top, _dev_ptr(out_i420, torch.uint8, n_frames * self.frame_bytes, "out_i420", self.device),
             _stream_handle(cuda_stream)), "lv_narrow_pictures")
 
+    def convert_diff_pictures(self, pic16, size_x, size_y, crop_left, crop_top, n_streams, n_frames, out, first_stream=0,
+                              cuda_stream=None):
+        """convert_diff_batch fed with decoder pictures (int16 CUDA tensor, narrow_pictures layout, stream-major): ONE
+        kernel narrows, crops, converts and differences (lv_convert_diff_pictures).  `out` as alloc_outputs gives it;
+        out["bgr"] is mandatory."""
+        import torch
+        n = n_streams * n_frames
+        d = self.device
+        samples = size_x * size_y + 2 * ((size_x // 2) * (size_y // 2))
+        capi.check(capi.lib().lv_convert_diff_pictures(
+            self._h, _dev_ptr(pic16, torch.int16, n * samples, "pic16", d), size_x, size_y, crop_left, crop_top, first_stream,
+            n_streams, n_frames, _dev_ptr(out.get("bgr"), torch.uint8, n * self.bgr_bytes, "bgr", d, 16),
+            _dev_ptr(out.get("mask_bits"), torch.int16, n * self.mask_units, "mask_bits", d),
+            _dev_ptr(out.get("mask_bytes"), torch.uint8, n * self.px, "mask_bytes", d, 16),
+            _dev_ptr(out.get("mb_count"), torch.int16, n * self.mbs, "mb_count", d),
+            _dev_ptr(out.get("mb_map"), torch.uint8, n * self.mbs, "mb_map", d),
+            _dev_ptr(out.get("summary"), torch.int32, 2 * n, "summary", d), _stream_handle(cuda_stream)),
+            "lv_convert_diff_pictures")
+
     def object_box_batch(self, masks, n_frames, x0, x1, y0, y1, mask_is_bits=False, cuda_stream=None):
         """One box per frame for n_frames masks laid out back to back: int32 CUDA tensor [n_frames, 4]."""
         import torch

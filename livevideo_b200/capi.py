@@ -48,6 +48,8 @@ SYMBOLS = {
     "lv_object_box": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "lv_object_box_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "lv_narrow_pictures": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "lv_convert_diff_pictures": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp,
+                                           _vp, _vp, _vp, _vp, _vp]),
     "lv_upload_async": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "lv_upload_wait": (C.c_int, [_vp, C.c_int, _vp]),
     "lv_upload_release": (C.c_int, [_vp, C.c_int, _vp]),

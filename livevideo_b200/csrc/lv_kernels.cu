@@ -54,6 +54,15 @@ struct KArgs {
     const int4 *windows;
     int4 *boxes;
     int n_obj;
+    // kPic instantiation only: the frames are the decoder's 16-bit pictures (imgpel = unsigned short, lib/JM/global.h:61;
+    // planes Y, U, V of size_x x size_y / quarter size, memalloc.c:26-39) and the kernel does what img2buf +
+    // write_out_picture do on the way (lib/JM/output.c:87-178, 362-453): low byte of every sample, crop cut away
+    const uint16_t *pic0;       // first picture
+    size_t pic_stride;          // samples between consecutive pictures
+    int size_x;                 // luma pitch in samples (chroma: size_x / 2)
+    uint32_t pic_y_off;         // crop_top * size_x + crop_left
+    uint32_t pic_c_off;         // size_x * size_y + (crop_top / 2) * (size_x / 2) + crop_left / 2
+    uint32_t pic_c_plane;       // (size_x / 2) * (size_y / 2): from U to V
 };
 
 // Cache policies (A/B measured on B200, profiles/README.md).  Loads: 0 = read-only path (ld.global.nc), 1 = .cs
@@ -126,6 +135,18 @@ __device__ __forceinline__ void st16_stream(uint8_t *p, const uint4 &v)
 #endif
 }
 
+// 16 (8) consecutive 16-bit samples -> their low bytes (img2buf keeps the first byte of every little-endian sample)
+__device__ __forceinline__ uint4 narrow16(const uint16_t *p)
+{
+    const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(p)), hi = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+    return make_uint4(prmt(lo.x, lo.y, 0x6420u), prmt(lo.z, lo.w, 0x6420u), prmt(hi.x, hi.y, 0x6420u), prmt(hi.z, hi.w, 0x6420u));
+}
+__device__ __forceinline__ uint2 narrow8(const uint16_t *p)
+{
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    return make_uint2(prmt(v.x, v.y, 0x6420u), prmt(v.z, v.w, 0x6420u));
+}
+
 // 16 pixels of one row: luma words yw[4], chroma samples c[8] -> 48 bytes
 __device__ __forceinline__ void convert_row16(const uint4 &y, const Chroma2 (&c)[8], uint8_t *dst)
 {
@@ -146,8 +167,8 @@ __device__ __forceinline__ void convert_row16(const uint4 &y, const Chroma2 (&c)
 // object's window, accumulated here so that no mask ever goes through HBM).
 constexpr int kMaxObjects = 16;
 
-template <bool kConv, bool kDiff, bool kMask, bool kBox = false>
-__global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
+template <bool kConv, bool kDiff, bool kMask, bool kBox = false, bool kPic = false>
+__global__ void __launch_bounds__(256, kPic ? 4 : LV_TILE_MINBLOCKS) k_tile(const KArgs a)
 {
     const Geom &g = a.g;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -180,17 +201,34 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
     if (active) {
         const uint8_t *yf = a.y0 + (size_t)f * a.y_stride;
         const uint32_t off = (uint32_t)row0 * (uint32_t)w + (uint32_t)unit * 16u;
-        const uint4 y0 = ld16(yf + off);          // re-read by the next frame as its reference: keep in L2
-        const uint4 y1 = ld16(yf + off + w);
+        [[maybe_unused]] const uint16_t *pf = nullptr;
+        [[maybe_unused]] uint32_t poff = 0;
+        uint4 y0, y1;
+        if constexpr (kPic) {
+            pf = a.pic0 + (size_t)f * a.pic_stride;
+            poff = a.pic_y_off + (uint32_t)row0 * (uint32_t)a.size_x + (uint32_t)unit * 16u;
+            y0 = narrow16(pf + poff);
+            y1 = narrow16(pf + poff + a.size_x);
+        } else {
+            y0 = ld16(yf + off);                  // re-read by the next frame as its reference: keep in L2
+            y1 = ld16(yf + off + w);
+        }
 
         if constexpr (kDiff) {
             const int s = a.n_frames == 1 ? f : (int)__umulhi((uint32_t)f, a.nf_magic);
             const int t = f - s * a.n_frames;
-            const uint8_t *ref;
-            if (a.ref_planes) ref = a.ref_planes + (size_t)f * g.px;
-            else ref = (t == 0 || a.static_ref) ? a.state_in + (size_t)s * g.px : yf - a.y_stride;
-            const uint4 p0 = ld16_stream(ref + off);
-            const uint4 p1 = ld16_stream(ref + off + w);
+            uint4 p0, p1;
+            if (kPic && !(t == 0 || a.static_ref)) {
+                // the previous PICTURE is the reference (block-uniform branch): narrowed again, from L2
+                p0 = narrow16(pf - a.pic_stride + poff);
+                p1 = narrow16(pf - a.pic_stride + poff + a.size_x);
+            } else {
+                const uint8_t *ref;
+                if (a.ref_planes) ref = a.ref_planes + (size_t)f * g.px;
+                else ref = (t == 0 || a.static_ref) ? a.state_in + (size_t)s * g.px : yf - a.y_stride;
+                p0 = ld16_stream(ref + off);
+                p1 = ld16_stream(ref + off + w);
+            }
             const uint32_t tol4 = (uint32_t)a.tol * 0x01010101u;
             const uint32_t ntol7 = ~tol4 & 0x7f7f7f7fu;
             if constexpr (kMask || kBox) {
@@ -220,10 +258,17 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
         }
 
         if constexpr (kConv) {
-            const uint8_t *uf = yf + g.px;
-            const uint32_t coff = (uint32_t)(row0 >> 1) * (uint32_t)(w >> 1) + (uint32_t)unit * 8u;
-            const uint2 u = ld8_stream(uf + coff);
-            const uint2 v = ld8_stream(uf + (g.px >> 2) + coff);
+            uint2 u, v;
+            if constexpr (kPic) {
+                const uint32_t pcoff = a.pic_c_off + (uint32_t)(row0 >> 1) * (uint32_t)(a.size_x >> 1) + (uint32_t)unit * 8u;
+                u = narrow8(pf + pcoff);
+                v = narrow8(pf + pcoff + a.pic_c_plane);
+            } else {
+                const uint8_t *uf = yf + g.px;
+                const uint32_t coff = (uint32_t)(row0 >> 1) * (uint32_t)(w >> 1) + (uint32_t)unit * 8u;
+                u = ld8_stream(uf + coff);
+                v = ld8_stream(uf + (g.px >> 2) + coff);
+            }
             Chroma2 c[8];
             c[0] = chroma_terms(ubyte<0>(u.x), ubyte<0>(v.x));
             c[1] = chroma_terms(ubyte<1>(u.x), ubyte<1>(v.x));
@@ -333,7 +378,7 @@ __global__ void __launch_bounds__(256, LV_TILE_MINBLOCKS) k_tile(const KArgs a)
     }
 }
 
-template <bool kConv, bool kDiff, bool kMask, bool kBox = false>
+template <bool kConv, bool kDiff, bool kMask, bool kBox = false, bool kPic = false>
 int launch_tile_t(const KArgs &a, int total_frames, cudaStream_t st)
 {
     int launches = 0;
@@ -351,7 +396,7 @@ int launch_tile_t(const KArgs &a, int total_frames, cudaStream_t st)
             b.mbw_magic = (uint32_t)(((1ULL << 32) + mbw - 1) / mbw);
             grid = dim3((unsigned)((mbs + 31) / 32), 1, nf);
         }
-        k_tile<kConv, kDiff, kMask, kBox><<<grid, block, 0, st>>>(b);
+        k_tile<kConv, kDiff, kMask, kBox, kPic><<<grid, block, 0, st>>>(b);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return -(int)e;
         launches++;
@@ -378,6 +423,10 @@ int launch_tile(KArgs a, int total_frames, cudaStream_t st)
     // the multiply-high division is exact for f < 2^16 and n_frames < 2^16; longer batches are cut by the caller
     a.nf_magic = a.n_frames > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)a.n_frames - 1) / (uint64_t)a.n_frames) : 0u;
     const bool mask = a.mask_bits || a.mask_bytes;
+    if constexpr (kConv && kDiff) {
+        if (a.pic0) return mask ? launch_tile_t<true, true, true, false, true>(a, total_frames, st)
+                                : launch_tile_t<true, true, false, false, true>(a, total_frames, st);
+    }
     if (kDiff && a.boxes) return launch_tile_t<kConv, kDiff, kDiff, kDiff>(a, total_frames, st);   // masks too, when asked
     if (kDiff && mask) return launch_tile_t<kConv, kDiff, kDiff>(a, total_frames, st);
     return launch_tile_t<kConv, kDiff, false>(a, total_frames, st);
@@ -439,9 +488,19 @@ int kernel_variant()
 void set_kernel_variant(int v) { g_variant = v == 1 ? 1 : 0; }
 static bool use_tma() { return kernel_variant() == 1; }
 
+// The fused picture kernel moves 16-byte words of 16-bit samples: luma rows, chroma rows, both chroma planes and every
+// picture must start on a multiple of 8 samples, and all offsets must fit the kernel's 32-bit arithmetic.
+bool pic_fusable(const Geom &g, const PicLayout &p)
+{
+    const size_t ypl = (size_t)p.size_x * p.size_y, cpl = (size_t)(p.size_x >> 1) * (p.size_y >> 1);
+    return p.pic16 && (reinterpret_cast<uintptr_t>(p.pic16) & 15) == 0 && p.size_x % 16 == 0 && p.crop_left % 16 == 0 &&
+           p.crop_top % 2 == 0 && ypl % 8 == 0 && cpl % 8 == 0 && p.samples % 8 == 0 && ypl + 2 * cpl < (1ull << 31) &&
+           p.crop_left + g.w <= p.size_x && p.crop_top + g.h <= p.size_y;
+}
+
 int launch_step(const StepArgs &s, cudaStream_t st)
 {
-    if (use_tma() && !s.static_ref && !s.boxes)
+    if (use_tma() && !s.static_ref && !s.boxes && !s.pic.pic16)
         if (int r = launch_step_tma(s, st)) return r;   // 0 = geometry/alignment not eligible for the TMA pipeline
     KArgs a{};
     a.static_ref = s.static_ref;
@@ -452,6 +511,17 @@ int launch_step(const StepArgs &s, cudaStream_t st)
     a.mb_count = s.mb_count; a.mb_map = s.mb_map; a.summary = s.summary;
     a.windows = reinterpret_cast<const int4 *>(s.windows); a.boxes = reinterpret_cast<int4 *>(s.boxes); a.n_obj = s.n_obj;
     if (s.boxes && (s.n_obj < 1 || s.n_obj > kMaxObjects || !s.windows)) return -(int)cudaErrorInvalidValue;
+    const PicLayout &pl = s.pic;
+    if (pl.pic16) {
+        // decoder pictures as input: conversion is mandatory (the chroma planes are only reachable through the kernel),
+        // boxes and the static-reference mode keep to the I420 form
+        if (!s.bgr || s.boxes || !pic_fusable(s.g, pl)) return -(int)cudaErrorInvalidValue;
+        a.pic0 = pl.pic16; a.pic_stride = pl.samples; a.size_x = pl.size_x;
+        a.pic_y_off = (uint32_t)pl.crop_top * (uint32_t)pl.size_x + (uint32_t)pl.crop_left;
+        a.pic_c_off = (uint32_t)pl.size_x * (uint32_t)pl.size_y + (uint32_t)(pl.crop_top >> 1) * (uint32_t)(pl.size_x >> 1) +
+                      (uint32_t)(pl.crop_left >> 1);
+        a.pic_c_plane = (uint32_t)(pl.size_x >> 1) * (uint32_t)(pl.size_y >> 1);
+    }
     if (s.n_frames > 65535) return -(int)cudaErrorInvalidValue;
     // the kernel's frame -> (stream, t) split is exact below 2^16 frames per launch group: cut by streams
     const int group = 65535 / s.n_frames;
@@ -462,6 +532,7 @@ int launch_step(const StepArgs &s, cudaStream_t st)
         const size_t f0 = (size_t)s0 * s.n_frames;
         KArgs b = a;
         b.y0 = a.y0 + f0 * s.g.frame;
+        if (a.pic0) b.pic0 = a.pic0 + f0 * a.pic_stride;
         b.state_in = a.state_in + (size_t)s0 * s.g.px;
         if (a.state_out) b.state_out = a.state_out + (size_t)s0 * s.g.px;
         if (a.bgr) b.bgr = a.bgr + f0 * 3 * s.g.px;

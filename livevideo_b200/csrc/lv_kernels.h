@@ -23,6 +23,15 @@ inline Geom make_geom(int w, int h)
     return g;
 }
 
+// Decoder pictures as the input of the fused step: 16-bit samples (imgpel = unsigned short, lib/JM/global.h:61), planes
+// Y (size_x x size_y), U, V (half size each way) back to back, `samples` apart; the frame is the crop window.
+struct PicLayout {
+    const uint16_t *pic16 = nullptr;
+    int size_x = 0, size_y = 0, crop_left = 0, crop_top = 0;
+    size_t samples = 0;
+};
+bool pic_fusable(const Geom &g, const PicLayout &p);
+
 // One launch of the fused step over n_streams*n_frames frames (stream-major).
 struct StepArgs {
     Geom g;
@@ -42,6 +51,7 @@ struct StepArgs {
     const int *windows;       // n_obj x {x0, x1, y0, y1} per frame, inclusive, 16-byte aligned
     int *boxes;               // n_obj x {min_x, max_x, min_y, max_y} per frame, 16-byte aligned
     int n_obj;                // 1 .. 16
+    PicLayout pic;            // pic.pic16 != NULL: the frames are decoder pictures (i420 unused, bgr mandatory, no boxes)
 };
 
 // difference of explicit (cur, ref) plane pairs: frame i of cur_y against frame i of ref_y

@@ -245,6 +245,57 @@ def test_zero_copy_entries_match_oracle_in_every_mode(lv, orc, torch_cuda, w, h)
             lv.host_unregister(a)
 
 
+# ---- decoder pictures straight into the fused kernel ------------------------------------------------------------------
+@pytest.mark.parametrize("sx,sy,cl,ct,w,h,ns,nf", [(1920, 1088, 0, 0, 1920, 1080, 1, 3), (384, 304, 16, 8, 352, 288, 2, 4),
+                                                   (64, 48, 0, 0, 64, 48, 3, 2), (1296, 736, 8, 6, 1280, 720, 1, 2),
+                                                   (96, 64, 32, 16, 64, 48, 2, 3), (560, 64, 16, 2, 528, 34, 1, 3)])
+def test_convert_diff_pictures_is_narrow_then_step(lv, orc, torch_cuda, sx, sy, cl, ct, w, h, ns, nf):
+    """lv_convert_diff_pictures (16-bit decoder pictures -> ONE kernel) == the reference's img2buf + write_out_picture
+    (lib/JM/output.c:87-178, 362-453) followed by the fused step, bit for bit: BGR, masks, counts, map, summary and the
+    carried state, over two calls (state carry), full 16-bit content (the upper byte is dropped, not clipped), layouts the
+    one-kernel path takes and one it does not (crop_left = 8: served through the scratch)."""
+    torch = torch_cuda
+    rng = np.random.default_rng(sx * 7 + w)
+    samples = sx * sy * 3 // 2
+    ctx = lv.Context(w, h, ns)
+    prev = np.zeros((ns, w * h), np.uint8)
+    px = w * h
+    n = ns * nf
+    for call in range(2):
+        pics = rng.integers(0, 65536, (ns, nf, samples), dtype=np.uint16)
+        pics[:, 1::2, :sx * sy] = (pics[:, 0:-1:2, :sx * sy] & 0xff00) | ((pics[:, 0:-1:2, :sx * sy] + rng.integers(0, 40, (ns, (nf) // 2, sx * sy), dtype=np.uint16)) & 0xff)
+        frames = np.stack([[orc.picture16_to_i420(pics[s, t], sx, sy, cl, sx - cl - w, ct, sy - ct - h) for t in range(nf)]
+                           for s in range(ns)])
+        prev_in = prev.copy()                           # the oracle advances `prev` in place
+        ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, 20, 0)
+        d_pic = torch.from_numpy(np.ascontiguousarray(pics).view(np.int16).reshape(-1)).cuda()
+        out = ctx.alloc_outputs(n, mask_bits=True, mask_bytes=True)
+        ctx.convert_diff_pictures(d_pic, sx, sy, cl, ct, ns, nf, out)
+        torch.cuda.synchronize()
+        assert np.array_equal(out["bgr"].cpu().numpy(), ref["bgr"]), call
+        assert np.array_equal(out["mask_bytes"].cpu().numpy(), ref["mask"]), call
+        bits = np.concatenate([orc.pack_mask16(ref["mask"][i * px:(i + 1) * px], w, h) for i in range(n)])
+        assert np.array_equal(out["mask_bits"].cpu().numpy().view(np.uint16), bits), call
+        assert np.array_equal(out["mb_count"].cpu().numpy().view(np.uint16), ref["mb_count"]), call
+        assert np.array_equal(out["mb_map"].cpu().numpy(), ref["mb_map"]), call
+        assert np.array_equal(out["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2), ref["summary"]), call
+        # without the masks (the common instantiation)
+        ctx2 = lv.Context(w, h, ns)
+        for s in range(ns):
+            ctx2.set_prev_luma(s, prev_in[s])
+        out2 = ctx2.alloc_outputs(n)
+        ctx2.convert_diff_pictures(d_pic, sx, sy, cl, ct, ns, nf, out2)
+        torch.cuda.synchronize()
+        assert np.array_equal(out2["bgr"].cpu().numpy(), ref["bgr"]) and np.array_equal(out2["mb_count"].cpu().numpy().view(np.uint16), ref["mb_count"])
+        ctx2.close()
+        prev = frames[:, -1, :px].copy()
+        for s in range(ns):
+            assert np.array_equal(ctx.get_prev_luma(s), prev[s]), (call, s)
+    with pytest.raises(lv.LiveVideoError):
+        ctx.convert_diff_pictures(d_pic, sx, sy, cl + 1, ct, ns, nf, out)        # odd crop
+    ctx.close()
+
+
 # ---- per-stream state -------------------------------------------------------------------------------------------------
 def test_partial_stream_steps_touch_no_other_state(lv, orc, torch_cuda):
     """Streams stepped in arbitrary sub-ranges and orders keep independent previous-luma state (image.c:1553-1561 per

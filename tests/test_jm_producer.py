@@ -95,7 +95,9 @@ def test_inprocess_hook_feeds_real_16bit_pictures(jm, orc, tmp_path, w, h, n, ba
     rep = json.loads(r.stdout.decode().strip().splitlines()[-1])
     assert rep["frames"] == n and rep["imgpel_bytes"] == 2
     assert rep["picture"] == [(w + 15) // 16 * 16, (h + 15) // 16 * 16]        # the decoder's own (uncropped) planes
-    assert rep["gpu_launches"] >= 2 * ((n + batch - 1) // batch)               # narrowing + fused kernel per batch
+    # one kernel per batch narrows, crops, converts and differences (macroblock-aligned decoder pictures always take the
+    # one-kernel form of lv_step_host_pictures); layouts it cannot take would show two
+    assert (n + batch - 1) // batch <= rep["gpu_launches"] <= 2 * ((n + batch - 1) // batch)
     prev = np.zeros((1, w * h), np.uint8)
     ref = orc.convert_diff_batch(frames[None], prev, 1, n, w, h, 20, 0, want_mask=False)
     assert np.array_equal(np.fromfile(prefix + ".bgr", np.uint8), ref["bgr"])

@@ -88,6 +88,13 @@ def main():
     pic = torch.randint(0, 1024, (n * (sx * sy * 3 // 2),), dtype=torch.int16, device="cuda")
     row("narrow_pictures (img2buf on device)", timeit(lambda: ctx.narrow_pictures(pic, n, sx, sy, 0, 0, o420)), 4.5,
         note=f"{sx}x{sy} 16-bit 4:2:0 in (3 B/px) + 1.5 B/px out")
+    outp = ctx.alloc_outputs(n)
+    row("narrow_pictures + fused step (2 kernels)", timeit(lambda: (ctx.narrow_pictures(pic, n, sx, sy, 0, 0, o420),
+                                                                      ctx.convert_diff_batch(o420, 1, n, outp))), 7.0,
+        note="algorithmic bytes of the ONE-kernel form: 3 in + 1 previous luma + 3 out")
+    row("fused step from 16-bit pictures (1 kernel)", timeit(lambda: ctx.convert_diff_pictures(pic, sx, sy, 0, 0, 1, n, outp)), 7.0,
+        note="3 B/px in (16-bit 4:2:0) + 1 B/px previous luma (2 B/px read from L2) + 3 B/px out; no I420 frame in memory")
+    del outp
     names = {1: "RGB24_to_YV12", 2: "YVU9_to_YV12", 3: "YUY2_to_YV12", 4: "YV12_to_YVU9", 5: "YV12_to_YUY2"}
     for kind in range(1, 6):
         ib, ob = L.lv_format_bytes(kind, w, h, 0), L.lv_format_bytes(kind, w, h, 1)
