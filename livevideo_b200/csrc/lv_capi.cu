@@ -1225,6 +1225,32 @@ int lv_diff_host_multi(const unsigned char *const *cur_y, const unsigned char *c
     const size_t off_cnt = pxa, off_map = off_cnt + ((2 * mbs + 15) & ~(size_t)15);
     const bool fast = geom_fast(width, height) && tol >= 0;
     const lv::Geom g = lv::make_geom(width, height);
+    if (zero_copy_mode() && fast && lv::kernel_variant() == 0) {
+        // every buffer of every picture pinned + mapped in place: the difference kernel addresses them directly, one launch
+        // per picture back to back on one stream, one synchronise
+        bool all = true;
+        for (int i = 0; i < n && all; i++) {
+            const uint8_t *c0 = mapped(cur_y[i], px), *r0 = mapped(ref_y[i], px);
+            all = c0 && r0 && aligned(c0, 16) && aligned(r0, 16);
+            if (all && mask && mask[i]) { const uint8_t *m0 = mapped(mask[i], px); all = m0 && aligned(m0, 16); }
+            if (all && mb_count && mb_count[i]) { const uint8_t *q = mapped(mb_count[i], 2 * mbs); all = q && aligned(q, 2); }
+            if (all && mb_map && mb_map[i]) all = mapped(mb_map[i], mbs) != nullptr;
+        }
+        if (all) {
+            for (int i = 0; i < n; i++) {
+                lv::DiffArgs a{};
+                a.g = g; a.n_frames = 1; a.tol = tol; a.mb_thresh = mb_thresh;
+                a.cur_y = mapped(cur_y[i], px); a.ref_y = mapped(ref_y[i], px);
+                a.mask_bytes = (mask && mask[i]) ? mapped(mask[i], px) : nullptr;
+                a.mb_count = (mb_count && mb_count[i]) ? reinterpret_cast<uint16_t *>(mapped(mb_count[i], 2 * mbs)) : nullptr;
+                a.mb_map = (mb_map && mb_map[i]) ? mapped(mb_map[i], mbs) : nullptr;
+                const int r = lv::launch_diff(a, P.s_k);
+                if (r < 0) return P.drain(cuda_fail((cudaError_t)(-r), "kernel launch"));
+            }
+            LV_MP(cudaStreamSynchronize(P.s_k));
+            return LV_OK;
+        }
+    }
     for (int i = 0; i < n; i++) {
         const int slot = i % MultiPipe::kSlots, pslot = (i + MultiPipe::kSlots - 1) % MultiPipe::kSlots;
         uint8_t *din = P.in[slot].get(2 * pxa), *dout = P.out[slot].get(off_map + mbs);

@@ -201,7 +201,10 @@ def test_zero_copy_entries_match_oracle_in_every_mode(lv, orc, torch_cuda, w, h)
         ys.append(y), us.append(u), vs.append(v), ds.append(d)
     mask, cnt, mp = _own(px), np.frombuffer(mmap.mmap(-1, 2 * 4096 * 4), dtype=np.uint16), _own(4096 * 4)
     mbs = ((w + 15) // 16) * ((h + 15) // 16)
-    bufs = ys + us + vs + ds + [mask, cnt, mp]
+    mmask = [_own(px) for _ in range(3)]
+    mcnt = [np.frombuffer(mmap.mmap(-1, 2 * 4096 * 4), dtype=np.uint16) for _ in range(3)]
+    mmap_ = [_own(4096 * 4) for _ in range(3)]
+    bufs = ys + us + vs + ds + [mask, cnt, mp] + mmask + mcnt + mmap_
     for a in bufs:
         lv.host_register(a)
     want = [orc.convert_frame(frames[i], w, h) for i in range(n)]
@@ -226,6 +229,13 @@ def test_zero_copy_entries_match_oracle_in_every_mode(lv, orc, torch_cuda, w, h)
             lv.FrameDiff_MB(ys[1], ys[0], w, h, 20, 0, mask=mask, mb_count=cnt[:mbs], mb_map=mp[:mbs])
             assert np.array_equal(mask, wm) and np.array_equal(cnt[:mbs], wc) and np.array_equal(mp[:mbs], wb), mode
             assert cnt[mbs] == 7 and mp[mbs] == 7                      # nothing written past the outputs
+            # the same over a sequence in one call (lv_diff_host_multi): every buffer registered
+            for m in mmask:
+                m[:] = 9
+            lv.FrameDiff_MB_multi(ys[1:4], ys[0:3], w, h, 20, 0, mask=mmask, mb_count=[c[:mbs] for c in mcnt], mb_map=[b[:mbs] for b in mmap_])
+            for i in range(3):
+                m_, c_, b_, _ = orc.frame_diff_mb(ys[i + 1], ys[i], w, h, 20, 0)
+                assert np.array_equal(mmask[i], m_) and np.array_equal(mcnt[i][:mbs], c_) and np.array_equal(mmap_[i][:mbs], b_), (mode, i)
         # one pageable destination / one plane at an odd offset: the staged path serves the call, same bytes
         lv.set_zero_copy("staged")
         pageable = np.zeros(3 * px, np.uint8)
