@@ -31,9 +31,12 @@ def main():
         top = sorted(((float(r[hdr.index(h)] or 0), h.split("stalled_")[1].split("_per")[0]) for h in stalls), reverse=True)[:6]
         print("  stalls per issue: " + ", ".join(f"{n} {v:.2f}" for v, n in top))
         try:
-            rd, wr = float(r[hdr.index("dram__bytes_read.sum")]), float(r[hdr.index("dram__bytes_write.sum")])
-            print(f"  => DRAM traffic {rd + wr:.1f} {units[hdr.index('dram__bytes_read.sum')]} per launch")
-        except (ValueError, IndexError):
+            # ncu picks a unit per metric AND per report (Mbyte for one, Gbyte for the other): normalise to MB
+            scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            rd, wr = float(r[ir]) * scale[units[ir]], float(r[iw]) * scale[units[iw]]
+            print(f"  => DRAM traffic {rd + wr:.1f} MB per launch ({rd:.1f} read + {wr:.1f} written)")
+        except (ValueError, IndexError, KeyError):
             pass
 
 
