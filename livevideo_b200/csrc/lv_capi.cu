@@ -559,7 +559,7 @@ int lv_convert_diff_pictures(lv_ctx *c, const uint16_t *d_pic16, int size_x, int
     lv::PicLayout p;
     p.pic16 = d_pic16; p.size_x = size_x; p.size_y = size_y; p.crop_left = crop_left; p.crop_top = crop_top;
     p.samples = (size_t)size_x * size_y + 2 * ((size_t)(size_x >> 1) * (size_y >> 1));
-    if (geom_fast(c->g.w, c->g.h) && lv::pic_fusable(c->g, p) && lv::kernel_variant() == 0)
+    if (geom_fast(c->g.w, c->g.h) && lv::pic_fusable(c->g, p) && lv::kernel_variant() != 1)
         return step_impl(c, nullptr, first_stream, n_streams, n_frames, d_bgr, d_mask_bits, d_mask_bytes, d_mb_count, d_mb_map,
                          d_summary, nullptr, 0, nullptr, cuda_stream, 0, &p);
     // a layout the fused kernel cannot take (odd pitches / crops, misaligned pictures): narrow into a scratch, then step
@@ -597,7 +597,7 @@ size_t lv_format_bytes(int kind, int width, int height, int output)
 
 int lv_set_kernel_variant(int variant)
 {
-    if (variant < 0 || variant > 1) return LV_E_ARG;
+    if (variant < 0 || variant > 3) return LV_E_ARG;
     lv::set_kernel_variant(variant);
     return LV_OK;
 }
@@ -821,7 +821,7 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
             if (pic) {
                 pl.pic16 = c->d_pic[slot]; pl.size_x = pic->size_x; pl.size_y = pic->size_y; pl.crop_left = pic->crop_left;
                 pl.crop_top = pic->crop_top; pl.samples = pic->samples;
-                fused = h_bgr && lv::pic_fusable(g, pl) && lv::kernel_variant() == 0;
+                fused = h_bgr && lv::pic_fusable(g, pl) && lv::kernel_variant() != 1;
                 if (!fused) {
                     rc = launch_result(lv::launch_narrow(g, c->d_pic[slot], ns * nt, pic->size_x, pic->size_y, pic->crop_left,
                                                          pic->crop_top, c->d_in[slot], c->s_compute), c->launches);
@@ -1018,7 +1018,7 @@ void FrameDiff_MB(const unsigned char *cur_y, const unsigned char *ref_y, int wi
     const size_t px = (size_t)width * height;
     const int mb_w = (width + 15) / 16, mb_h = (height + 15) / 16;
     const size_t mbs = (size_t)mb_w * mb_h;
-    if (zero_copy_mode() && geom_fast(width, height) && tol >= 0 && lv::kernel_variant() == 0) {
+    if (zero_copy_mode() && geom_fast(width, height) && tol >= 0 && lv::kernel_variant() != 1) {
         // the planes (and the byte mask) pinned + mapped in place: the difference kernel addresses them directly; the two
         // small per-macroblock outputs go the same way when they are mapped too, else through the device scratch
         lv::DiffArgs a{};
@@ -1225,7 +1225,7 @@ int lv_diff_host_multi(const unsigned char *const *cur_y, const unsigned char *c
     const size_t off_cnt = pxa, off_map = off_cnt + ((2 * mbs + 15) & ~(size_t)15);
     const bool fast = geom_fast(width, height) && tol >= 0;
     const lv::Geom g = lv::make_geom(width, height);
-    if (zero_copy_mode() && fast && lv::kernel_variant() == 0) {
+    if (zero_copy_mode() && fast && lv::kernel_variant() != 1) {
         // every buffer of every picture pinned + mapped in place: the difference kernel addresses them directly, one launch
         // per picture back to back on one stream, one synchronise
         bool all = true;
