@@ -496,7 +496,7 @@ def host_unregister(a):
     capi.check(capi.lib().lv_host_unregister(a.ctypes.data), "lv_host_unregister")
 
 
-KERNEL_VARIANTS = {"tile": 0, "tma": 1, "rows": 2, "rows2": 3}
+KERNEL_VARIANTS = {"tile": 0, "tma": 1}
 
 
 def set_kernel_variant(name):

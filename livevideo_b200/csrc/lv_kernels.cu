@@ -63,7 +63,6 @@ struct KArgs {
     uint32_t pic_y_off;         // crop_top * size_x + crop_left
     uint32_t pic_c_off;         // size_x * size_y + (crop_top / 2) * (size_x / 2) + crop_left / 2
     uint32_t pic_c_plane;       // (size_x / 2) * (size_y / 2): from U to V
-    int rows_variant;           // host side only: 0 = k_tile, 1 = k_rows<false>, 2 = k_rows<true>
 };
 
 // Cache policies (A/B measured on B200, profiles/README.md).  Loads: 0 = read-only path (ld.global.nc), 1 = .cs
@@ -379,122 +378,6 @@ __global__ void __launch_bounds__(256, kPic ? 4 : LV_TILE_MINBLOCKS) k_tile(cons
     }
 }
 
-// ---- one row per thread (experimental variants 2 / 3 of the fused step) ------------------------------------------------
-// Same block tile as k_tile (512 px x 16 rows = 32 macroblocks of one macroblock row) but 16 warps, each thread owning 16
-// pixels of ONE row: every warp request covers a single row segment, the access shape tools/ubench/mempat.cu measured
-// fastest (P12).  The price is the chroma: the two rows of a pair need the same 8 chroma samples.
-//   kShare = false : both rows compute all 8 samples' terms
-//   kShare = true  : the even row's warp computes samples 0..3, the odd row's samples 4..7; the 2 x 12 words change hands
-//                    through shared memory behind a 64-thread named barrier (one per row pair)
-template <bool kShare>
-__global__ void __launch_bounds__(512, 3) k_rows(const KArgs a)
-{
-    const Geom &g = a.g;
-    const int tx = threadIdx.x, ty = threadIdx.y;          // ty = row inside the macroblock row
-    int unit, mby;
-    if (a.mbw_magic) {
-        const int m = blockIdx.x * 32 + tx;
-        mby = (int)__umulhi((uint32_t)m, a.mbw_magic);
-        unit = m - mby * g.mb_w;
-    } else {
-        unit = blockIdx.x * 32 + tx;
-        mby = blockIdx.y;
-    }
-    const int row = mby * 16 + ty;
-    const int f = a.f_base + blockIdx.z;
-    const bool active = unit < g.units && row < g.h;
-    const int w = g.w;
-    __shared__ uint4 cx[kShare ? 8 : 1][kShare ? 2 : 1][kShare ? 3 : 1][32];
-
-    uint32_t cnt = 0;
-    uint4 y = make_uint4(0, 0, 0, 0);
-    uint2 u = make_uint2(0, 0), v = make_uint2(0, 0);
-    const uint8_t *yf = a.y0 + (size_t)f * a.y_stride;
-    const uint32_t off = (uint32_t)row * (uint32_t)w + (uint32_t)unit * 16u;
-    if (active) {
-        y = ld16(yf + off);
-        const uint32_t coff = (uint32_t)(row >> 1) * (uint32_t)(w >> 1) + (uint32_t)unit * 8u;
-        u = ld8_stream(yf + g.px + coff);
-        v = ld8_stream(yf + g.px + (g.px >> 2) + coff);
-        const int s = a.n_frames == 1 ? f : (int)__umulhi((uint32_t)f, a.nf_magic);
-        const int t = f - s * a.n_frames;
-        const uint8_t *ref = (t == 0 || a.static_ref) ? a.state_in + (size_t)s * g.px : yf - a.y_stride;
-        const uint4 p = ld16_stream(ref + off);
-        const uint32_t tol4 = (uint32_t)a.tol * 0x01010101u;
-        const uint32_t ntol7 = ~tol4 & 0x7f7f7f7fu;
-        cnt = diff_count16(y, p, tol4, ntol7, 0u);
-        if (a.state_out && t == a.n_frames - 1)
-            *reinterpret_cast<uint4 *>(a.state_out + (size_t)s * g.px + off) = y;
-    }
-    Chroma2 c[8];
-    if constexpr (kShare) {
-        // my half of the pair's chroma samples: even row -> samples 0..3 (u.x, v.x), odd row -> 4..7 (u.y, v.y)
-        const int odd = ty & 1;
-        const uint32_t uw = odd ? u.y : u.x, vw = odd ? v.y : v.x;
-        Chroma2 m[4];
-        m[0] = chroma_terms(ubyte<0>(uw), ubyte<0>(vw));
-        m[1] = chroma_terms(ubyte<1>(uw), ubyte<1>(vw));
-        m[2] = chroma_terms(ubyte<2>(uw), ubyte<2>(vw));
-        m[3] = chroma_terms(ubyte<3>(uw), ubyte<3>(vw));
-        uint4 (*slot)[3][32] = cx[ty >> 1];
-        slot[odd][0][tx] = make_uint4(m[0].cb2, m[0].ng2, m[0].cr2, m[1].cb2);
-        slot[odd][1][tx] = make_uint4(m[1].ng2, m[1].cr2, m[2].cb2, m[2].ng2);
-        slot[odd][2][tx] = make_uint4(m[2].cr2, m[3].cb2, m[3].ng2, m[3].cr2);
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + (ty >> 1)) : "memory");
-        // all eight back from shared memory (own half included: no selects on the row's parity)
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-            const uint4 q0 = slot[hh][0][tx], q1 = slot[hh][1][tx], q2 = slot[hh][2][tx];
-            Chroma2 *o = c + 4 * hh;
-            o[0].cb2 = q0.x; o[0].ng2 = q0.y; o[0].cr2 = q0.z; o[1].cb2 = q0.w;
-            o[1].ng2 = q1.x; o[1].cr2 = q1.y; o[2].cb2 = q1.z; o[2].ng2 = q1.w;
-            o[2].cr2 = q2.x; o[3].cb2 = q2.y; o[3].ng2 = q2.z; o[3].cr2 = q2.w;
-        }
-    } else {
-        c[0] = chroma_terms(ubyte<0>(u.x), ubyte<0>(v.x));
-        c[1] = chroma_terms(ubyte<1>(u.x), ubyte<1>(v.x));
-        c[2] = chroma_terms(ubyte<2>(u.x), ubyte<2>(v.x));
-        c[3] = chroma_terms(ubyte<3>(u.x), ubyte<3>(v.x));
-        c[4] = chroma_terms(ubyte<0>(u.y), ubyte<0>(v.y));
-        c[5] = chroma_terms(ubyte<1>(u.y), ubyte<1>(v.y));
-        c[6] = chroma_terms(ubyte<2>(u.y), ubyte<2>(v.y));
-        c[7] = chroma_terms(ubyte<3>(u.y), ubyte<3>(v.y));
-    }
-    if (active) {
-        uint8_t *d = a.bgr + (size_t)f * 3 * g.px + ((uint32_t)(g.h - 1 - row) * 3u * (uint32_t)w + (uint32_t)unit * 48u);
-        convert_row16(y, c, d);
-    }
-
-    __shared__ uint32_t part[16][32];
-    part[ty][tx] = cnt;
-    __syncthreads();
-    if (ty == 0) {
-        uint32_t tot = 0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) tot += part[i][tx];
-        tot >>= 7;
-        const bool valid = unit < g.units && mby < g.mb_h;
-        const uint32_t on = valid && (int)tot > a.mb_thresh;
-        if (valid) {
-            const size_t k = (size_t)f * g.mb_w * g.mb_h + (size_t)mby * g.mb_w + unit;
-            if (a.mb_count) a.mb_count[k] = (uint16_t)tot;
-            if (a.mb_map) a.mb_map[k] = (uint8_t)on;
-        }
-        if (a.summary) {
-            uint32_t spx = valid ? tot : 0, smb = on;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                spx += __shfl_xor_sync(0xffffffffu, spx, o);
-                smb += __shfl_xor_sync(0xffffffffu, smb, o);
-            }
-            if (tx == 0) {
-                if (spx) atomicAdd(a.summary + 2 * (size_t)f, spx);
-                if (smb) atomicAdd(a.summary + 2 * (size_t)f + 1, smb);
-            }
-        }
-    }
-}
-
 template <bool kConv, bool kDiff, bool kMask, bool kBox = false, bool kPic = false>
 int launch_tile_t(const KArgs &a, int total_frames, cudaStream_t st)
 {
@@ -513,11 +396,6 @@ int launch_tile_t(const KArgs &a, int total_frames, cudaStream_t st)
             b.mbw_magic = (uint32_t)(((1ULL << 32) + mbw - 1) / mbw);
             grid = dim3((unsigned)((mbs + 31) / 32), 1, nf);
         }
-        if (kConv && kDiff && !kMask && !kBox && !kPic && b.rows_variant) {
-            block = dim3(32, 16);
-            if (b.rows_variant == 2) k_rows<true><<<grid, block, 0, st>>>(b);
-            else k_rows<false><<<grid, block, 0, st>>>(b);
-        } else
         k_tile<kConv, kDiff, kMask, kBox, kPic><<<grid, block, 0, st>>>(b);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return -(int)e;
@@ -603,11 +481,11 @@ int kernel_variant()
 {
     if (g_variant < 0) {
         const char *e = getenv("LV_KERNEL");
-        g_variant = (e && e[0] == 't' && e[1] == 'm') ? 1 : (e && e[0] == 'r' && e[1] == 'o') ? (e[4] == '2' ? 3 : 2) : 0;
+        g_variant = (e && e[0] == 't' && e[1] == 'm') ? 1 : 0;
     }
     return g_variant;
 }
-void set_kernel_variant(int v) { g_variant = (v >= 0 && v <= 3) ? v : 0; }
+void set_kernel_variant(int v) { g_variant = v == 1 ? 1 : 0; }
 static bool use_tma() { return kernel_variant() == 1; }
 
 // The fused picture kernel moves 16-byte words of 16-bit samples: luma rows, chroma rows, both chroma planes and every
@@ -625,7 +503,6 @@ int launch_step(const StepArgs &s, cudaStream_t st)
     if (use_tma() && !s.static_ref && !s.boxes && !s.pic.pic16)
         if (int r = launch_step_tma(s, st)) return r;   // 0 = geometry/alignment not eligible for the TMA pipeline
     KArgs a{};
-    a.rows_variant = kernel_variant() >= 2 ? kernel_variant() - 1 : 0;
     a.static_ref = s.static_ref;
     a.g = s.g; a.y0 = s.i420; a.y_stride = s.g.frame; a.ref_planes = nullptr;
     a.state_in = s.state_in; a.state_out = s.state_out; a.n_frames = s.n_frames;
