@@ -304,7 +304,8 @@ LV_API int lv_shard_sync(lv_shard *s);
 
 /* ---- kernel variant (process-wide) -------------------------------------------------------------------
  * 0 = tiled kernel (default), 1 = TMA pipeline (cp.async.bulk.tensor loads/stores; measured slower, kept as the one
- * selectable alternative).  Both are bit-identical; the choice only affects speed (DESIGN.md has the measurements). */
+ * selectable alternative), 2 / 3 = tiled kernel with its chroma loads forced late / early (0 picks by row length: early up
+ * to 2048 pixels per row).  All are bit-identical; the choice only affects speed (DESIGN.md has the measurements). */
 LV_API int lv_set_kernel_variant(int variant);
 LV_API int lv_get_kernel_variant(void);
 

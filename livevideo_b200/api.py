@@ -496,11 +496,12 @@ def host_unregister(a):
     capi.check(capi.lib().lv_host_unregister(a.ctypes.data), "lv_host_unregister")
 
 
-KERNEL_VARIANTS = {"tile": 0, "tma": 1}
+KERNEL_VARIANTS = {"tile": 0, "tma": 1, "tile_late": 2, "tile_early": 3}
 
 
 def set_kernel_variant(name):
-    """Select the kernel variant ("tile" default, "tma"); both are bit-identical."""
+    """Select the kernel variant ("tile" default, "tma", "tile_late" / "tile_early" = tile with one order of its chroma
+    loads forced); all are bit-identical."""
     capi.check(capi.lib().lv_set_kernel_variant(KERNEL_VARIANTS[name]), "lv_set_kernel_variant")
 
 

@@ -597,7 +597,7 @@ size_t lv_format_bytes(int kind, int width, int height, int output)
 
 int lv_set_kernel_variant(int variant)
 {
-    if (variant < 0 || variant > 1) return LV_E_ARG;
+    if (variant < 0 || variant > 3) return LV_E_ARG;
     lv::set_kernel_variant(variant);
     return LV_OK;
 }

@@ -167,7 +167,11 @@ __device__ __forceinline__ void convert_row16(const uint4 &y, const Chroma2 (&c)
 // object's window, accumulated here so that no mask ever goes through HBM).
 constexpr int kMaxObjects = 16;
 
-template <bool kConv, bool kDiff, bool kMask, bool kBox = false, bool kPic = false>
+//
+// kEarly (plain fused instantiation only): the chroma loads are issued right behind the luma loads, in front of the
+// reference-luma loads, instead of after the difference.  Same instructions, same bytes, different order of the six loads
+// -- and this kernel's speed follows that order: see launch_fused_plain() for which pictures take which.
+template <bool kConv, bool kDiff, bool kMask, bool kBox = false, bool kPic = false, bool kEarly = false>
 __global__ void __launch_bounds__(256, kPic ? 4 : LV_TILE_MINBLOCKS) k_tile(const KArgs a)
 {
     const Geom &g = a.g;
@@ -212,6 +216,12 @@ __global__ void __launch_bounds__(256, kPic ? 4 : LV_TILE_MINBLOCKS) k_tile(cons
         } else {
             y0 = ld16(yf + off);                  // re-read by the next frame as its reference: keep in L2
             y1 = ld16(yf + off + w);
+        }
+        [[maybe_unused]] uint2 u_early = make_uint2(0, 0), v_early = make_uint2(0, 0);
+        if constexpr (kEarly && kConv && !kPic) {
+            const uint32_t coff = (uint32_t)(row0 >> 1) * (uint32_t)(w >> 1) + (uint32_t)unit * 8u;
+            u_early = ld8_stream(yf + g.px + coff);
+            v_early = ld8_stream(yf + g.px + (g.px >> 2) + coff);
         }
 
         if constexpr (kDiff) {
@@ -263,6 +273,9 @@ __global__ void __launch_bounds__(256, kPic ? 4 : LV_TILE_MINBLOCKS) k_tile(cons
                 const uint32_t pcoff = a.pic_c_off + (uint32_t)(row0 >> 1) * (uint32_t)(a.size_x >> 1) + (uint32_t)unit * 8u;
                 u = narrow8(pf + pcoff);
                 v = narrow8(pf + pcoff + a.pic_c_plane);
+            } else if constexpr (kEarly) {
+                u = u_early;
+                v = v_early;
             } else {
                 const uint8_t *uf = yf + g.px;
                 const uint32_t coff = (uint32_t)(row0 >> 1) * (uint32_t)(w >> 1) + (uint32_t)unit * 8u;
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(256, kPic ? 4 : LV_TILE_MINBLOCKS) k_tile(cons
     }
 }
 
-template <bool kConv, bool kDiff, bool kMask, bool kBox = false, bool kPic = false>
+template <bool kConv, bool kDiff, bool kMask, bool kBox = false, bool kPic = false, bool kEarly = false>
 int launch_tile_t(const KArgs &a, int total_frames, cudaStream_t st)
 {
     int launches = 0;
@@ -396,7 +409,7 @@ int launch_tile_t(const KArgs &a, int total_frames, cudaStream_t st)
             b.mbw_magic = (uint32_t)(((1ULL << 32) + mbw - 1) / mbw);
             grid = dim3((unsigned)((mbs + 31) / 32), 1, nf);
         }
-        k_tile<kConv, kDiff, kMask, kBox, kPic><<<grid, block, 0, st>>>(b);
+        k_tile<kConv, kDiff, kMask, kBox, kPic, kEarly><<<grid, block, 0, st>>>(b);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return -(int)e;
         launches++;
@@ -416,6 +429,24 @@ __global__ void k_step_init(uint32_t *summary, int n_summary_words, const int4 *
     }
 }
 
+// ---- order of the six loads of the plain fused kernel --------------------------------------------------------------------
+// Measured on three B200 boards (profiles/r02_ab_kernel_variants.txt, "load order"): chroma loads issued early are 1.5 % faster
+// at 1080p and 1.7 - 2 % at 720p on every board; at 4K the same order is bimodal (213 us or 235 - 245 us from one round of 30
+// launches to the next, against a steady 218 - 220 us for the late order).  So the rule is static and by row length; a run-time
+// tuner that timed both instantiations on the caller's first launches was built and dropped (the 4K bimodality defeats a
+// handful of samples).  lv_set_kernel_variant(2 / 3) or LV_LOAD_ORDER=0 / 1 force one order (tests, A/B runs).
+int launch_fused_plain(const KArgs &a, int total_frames, cudaStream_t st)
+{
+    static const int forced = [] {
+        const char *s = getenv("LV_LOAD_ORDER");
+        return (s && (s[0] == '0' || s[0] == '1') && !s[1]) ? s[0] - '0' : -1;
+    }();
+    const int var = kernel_variant();
+    const bool early = var >= 2 ? var == 3 : forced >= 0 ? forced == 1 : a.g.w <= 2048;
+    return early ? launch_tile_t<true, true, false, false, false, true>(a, total_frames, st)
+                 : launch_tile_t<true, true, false>(a, total_frames, st);
+}
+
 template <bool kConv, bool kDiff>
 int launch_tile(KArgs a, int total_frames, cudaStream_t st)
 {
@@ -429,6 +460,7 @@ int launch_tile(KArgs a, int total_frames, cudaStream_t st)
     }
     if (kDiff && a.boxes) return launch_tile_t<kConv, kDiff, kDiff, kDiff>(a, total_frames, st);   // masks too, when asked
     if (kDiff && mask) return launch_tile_t<kConv, kDiff, kDiff>(a, total_frames, st);
+    if constexpr (kConv && kDiff) return launch_fused_plain(a, total_frames, st);
     return launch_tile_t<kConv, kDiff, false>(a, total_frames, st);
 }
 
@@ -474,7 +506,8 @@ __global__ void k_diff_generic(int w, int h, const uint8_t *__restrict__ cur, co
 }  // namespace
 
 // Kernel variant: 0 = tiled (default, fastest: profiles/), 1 = TMA pipeline (the one measured-and-rejected design kept
-// selectable).  Both produce identical bytes (tests/test_gpu_parity.py runs the parity suite over each).  The
+// selectable), 2 / 3 = tiled with the late / early order of the chroma loads forced (0 picks by row length, see
+// launch_fused_plain).  All produce identical bytes (tests/test_gpu_parity.py runs the parity suite over each).  The
 // environment variable LV_KERNEL=tile|tma sets the initial value; lv_set_kernel_variant() overrides it.
 static int g_variant = -1;
 int kernel_variant()
@@ -485,7 +518,7 @@ int kernel_variant()
     }
     return g_variant;
 }
-void set_kernel_variant(int v) { g_variant = v == 1 ? 1 : 0; }
+void set_kernel_variant(int v) { g_variant = v >= 1 && v <= 3 ? v : 0; }
 static bool use_tma() { return kernel_variant() == 1; }
 
 // The fused picture kernel moves 16-byte words of 16-bit samples: luma rows, chroma rows, both chroma planes and every

@@ -396,7 +396,7 @@ def test_object_box_batch_matches_reference_scan(lv, orc, torch_cuda, w, h):
 
 # ---- every kernel variant computes the same bytes --------------------------------------------------------------
 
-@pytest.mark.parametrize("variant", ["tile", "tma"])
+@pytest.mark.parametrize("variant", ["tile", "tma", "tile_late", "tile_early"])
 def test_kernel_variants_are_bit_identical(lv, orc, torch_cuda, variant):
     """tile (default) and the TMA pipeline, over aligned, ragged and partial-band geometries,
     with and without the mask outputs, plus the conversion-only and difference-only entries."""
