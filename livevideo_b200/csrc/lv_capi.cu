@@ -63,6 +63,13 @@ struct lv_ctx {
     uint32_t *d_sum[kSlots] = {};
     cudaEvent_t ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
     int slot_frames = 0;                      // capacity of one slot in frames
+    // the small outputs (macroblock counts / map, summaries) of a WHOLE host step, in the caller's layout: one download
+    // per array behind the last chunk instead of three small copies between the picture downloads of every chunk
+    uint16_t *d_step_cnt = nullptr;
+    uint8_t *d_step_map = nullptr;
+    uint32_t *d_step_sum = nullptr;
+    size_t step_frames = 0;                   // their capacity in frames
+    cudaEvent_t ev_small = nullptr;
     uint16_t *d_pic[kSlots] = {};             // lv_step_host_pictures: raw 16-bit pictures of a chunk
     uint8_t *d_narrow = nullptr;              // lv_convert_diff_pictures, layouts the fused kernel cannot take: I420 scratch
     size_t narrow_cap = 0;
@@ -175,6 +182,43 @@ void free_pipeline(lv_ctx *c)
     c->s_copy_in = c->s_compute = c->s_copy_out = nullptr;
     c->slot_frames = 0;
     c->pic_cap = 0;
+    cudaFree(c->d_step_cnt); cudaFree(c->d_step_map); cudaFree(c->d_step_sum);
+    c->d_step_cnt = nullptr; c->d_step_map = nullptr; c->d_step_sum = nullptr;
+    c->step_frames = 0;
+    if (c->ev_small) cudaEventDestroy(c->ev_small);
+    c->ev_small = nullptr;
+}
+
+// Whole-step staging of the small outputs: `frames` = every frame of one host step.
+int ensure_step_small(lv_ctx *c, size_t frames)
+{
+    if (!c->ev_small) LV_CUDA(cudaEventCreateWithFlags(&c->ev_small, cudaEventDisableTiming));
+    if (c->step_frames >= frames) return LV_OK;
+    cudaFree(c->d_step_cnt); cudaFree(c->d_step_map); cudaFree(c->d_step_sum);
+    c->d_step_cnt = nullptr; c->d_step_map = nullptr; c->d_step_sum = nullptr;
+    c->step_frames = 0;
+    const size_t mbs = (size_t)c->g.mb_w * c->g.mb_h;
+    LV_CUDA(cudaMalloc(&c->d_step_cnt, sizeof(uint16_t) * mbs * frames));
+    LV_CUDA(cudaMalloc(&c->d_step_map, mbs * frames));
+    LV_CUDA(cudaMalloc(&c->d_step_sum, sizeof(uint32_t) * 2 * frames));
+    c->step_frames = frames;
+    return LV_OK;
+}
+
+// A chunk of `ns` streams x `nt` frames wrote its small outputs chunk-major into a slot; the caller's arrays are
+// stream-major over the whole step (`n_frames` frames per stream).  One block per frame of the chunk; dst pointers are
+// already offset to the chunk's first frame.
+__global__ void k_place_small(const uint16_t *__restrict__ cnt_src, uint16_t *__restrict__ cnt_dst,
+                              const uint8_t *__restrict__ map_src, uint8_t *__restrict__ map_dst,
+                              const uint32_t *__restrict__ sum_src, uint32_t *__restrict__ sum_dst, int mbs, int nt, int n_frames)
+{
+    const int f = blockIdx.x, s = f / nt, t = f - s * nt;
+    const size_t src = (size_t)f * mbs, dst = ((size_t)s * n_frames + t) * mbs;
+    for (int i = threadIdx.x; i < mbs; i += blockDim.x) {
+        if (cnt_src) cnt_dst[dst + i] = cnt_src[src + i];
+        if (map_src) map_dst[dst + i] = map_src[src + i];
+    }
+    if (sum_src && threadIdx.x < 2) sum_dst[((size_t)s * n_frames + t) * 2 + threadIdx.x] = sum_src[(size_t)f * 2 + threadIdx.x];
 }
 
 // Device slots for the host step: `frames` frames each.
@@ -762,6 +806,11 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
         rc = ensure_pic_slots(c, pic->samples * (size_t)cs * cf);
         if (rc != LV_OK) return rc;
     }
+    const bool small = h_mb_count || h_mb_map || h_summary;
+    if (small) {
+        rc = ensure_step_small(c, (size_t)n_streams * n_frames);
+        if (rc != LV_OK) return rc;
+    }
 
     // A chunk is `ns` runs of `nt` consecutive frames, `n_frames` frames apart in the host batch.  One strided copy moves
     // it when both pitches fit the device's limit (cudaMemcpy2DAsync rejects larger ones: 2 GiB - 1 on B200, i.e. 87
@@ -794,10 +843,19 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
     } while (0)
 
     int k = 0;
+    const char *ramp_env = getenv("LV_HOST_RAMP");
+    const bool ramp_on = !(ramp_env && ramp_env[0] == '0');
+    const size_t ramp_in = in_frame * (size_t)cs;                       // input bytes of one frame of every stream in a chunk
+    const int ramp0 = ramp_in >= ((size_t)1 << 20) ? 1 : (int)((((size_t)1 << 20) + ramp_in - 1) / ramp_in);   // >= 1 MiB
     for (int s0 = 0; s0 < n_streams; s0 += cs) {
         const int ns = n_streams - s0 < cs ? n_streams - s0 : cs;
-        for (int t0 = 0; t0 < n_frames; t0 += cf, k++) {
-            const int nt = n_frames - t0 < cf ? n_frames - t0 : cf;
+        // the first chunks of a step ramp up (1, 2, 4 ... frames, at least 1 MiB of input): nothing can be downloaded
+        // before the first chunk has been uploaded and computed, so the pipeline is filled with a small one
+        int ramp = s0 == 0 && ramp_on ? ramp0 : cf;
+        for (int t0 = 0, nt = 0; t0 < n_frames; t0 += nt, k++) {
+            nt = ramp < cf ? ramp : cf;
+            if (nt > n_frames - t0) nt = n_frames - t0;
+            ramp = ramp < cf ? ramp * 2 : cf;
             const int slot = k % lv_ctx::kSlots;
             // the slot's previous download must have drained before its buffers are reused
             if (k >= lv_ctx::kSlots) {
@@ -828,11 +886,22 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
                     if (rc != LV_OK) return bail(rc);
                 }
             }
+            // small outputs: straight into the whole-step arrays when the chunk is one run there (a single stream, or
+            // every frame of its streams), else into the slot and placed by a tiny kernel behind the step
+            const bool direct = ns == 1 || nt == n_frames;
+            uint16_t *k_cnt = !h_mb_count ? nullptr : direct ? c->d_step_cnt + hf * mbs : c->d_cnt[slot];
+            uint8_t *k_map = !h_mb_map ? nullptr : direct ? c->d_step_map + hf * mbs : c->d_map[slot];
+            uint32_t *k_sum = !h_summary ? nullptr : direct ? c->d_step_sum + hf * 2 : c->d_sum[slot];
             rc = step_impl(c, fused ? nullptr : c->d_in[slot], first_stream + s0, ns, nt, h_bgr ? c->d_bgr[slot] : nullptr,
-                           h_mask_bits ? c->d_bits[slot] : nullptr, nullptr, h_mb_count ? c->d_cnt[slot] : nullptr,
-                           h_mb_map ? c->d_map[slot] : nullptr, h_summary ? c->d_sum[slot] : nullptr, nullptr, 0, nullptr,
+                           h_mask_bits ? c->d_bits[slot] : nullptr, nullptr, k_cnt, k_map, k_sum, nullptr, 0, nullptr,
                            c->s_compute, 0, fused ? &pl : nullptr);
             if (rc != LV_OK) return bail(rc);
+            if (small && !direct) {
+                k_place_small<<<ns * nt, 256, 0, c->s_compute>>>(k_cnt, c->d_step_cnt + hf * mbs, k_map, c->d_step_map + hf * mbs, k_sum,
+                                                              c->d_step_sum + hf * 2, (int)mbs, nt, n_frames);
+                LV_PIPE(cudaGetLastError());
+                c->launches++;
+            }
             LV_PIPE(cudaEventRecord(c->ev_k[slot], c->s_compute));
             LV_PIPE(cudaStreamWaitEvent(c->s_copy_out, c->ev_k[slot], 0));
             // D2H: the same strided shape per output (width = this chunk's nt frames of one stream, rows = streams)
@@ -842,14 +911,22 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
             };
             if (h_bgr) LV_PIPE(down(h_bgr, c->d_bgr[slot], 3 * g.px));
             if (h_mask_bits) LV_PIPE(down(h_mask_bits, c->d_bits[slot], sizeof(uint16_t) * units));
-            if (h_mb_count) LV_PIPE(down(h_mb_count, c->d_cnt[slot], sizeof(uint16_t) * mbs));
-            if (h_mb_map) LV_PIPE(down(h_mb_map, c->d_map[slot], mbs));
-            if (h_summary) LV_PIPE(down(h_summary, c->d_sum[slot], sizeof(uint32_t) * 2));
             LV_PIPE(cudaEventRecord(c->ev_out[slot], c->s_copy_out));
         }
     }
-    LV_CUDA(cudaStreamSynchronize(c->s_copy_out));
-    LV_CUDA(cudaStreamSynchronize(c->s_compute));
+    // the small outputs of the whole step: one copy per array, on the upload stream (idle by now), beside the last
+    // picture downloads
+    if (small) {
+        const size_t frames = (size_t)n_streams * n_frames;
+        LV_PIPE(cudaEventRecord(c->ev_small, c->s_compute));
+        LV_PIPE(cudaStreamWaitEvent(c->s_copy_in, c->ev_small, 0));
+        if (h_mb_count) LV_PIPE(cudaMemcpyAsync(h_mb_count, c->d_step_cnt, sizeof(uint16_t) * mbs * frames, cudaMemcpyDeviceToHost, c->s_copy_in));
+        if (h_mb_map) LV_PIPE(cudaMemcpyAsync(h_mb_map, c->d_step_map, mbs * frames, cudaMemcpyDeviceToHost, c->s_copy_in));
+        if (h_summary) LV_PIPE(cudaMemcpyAsync(h_summary, c->d_step_sum, sizeof(uint32_t) * 2 * frames, cudaMemcpyDeviceToHost, c->s_copy_in));
+    }
+    LV_PIPE(cudaStreamSynchronize(c->s_copy_out));
+    LV_PIPE(cudaStreamSynchronize(c->s_copy_in));
+    LV_PIPE(cudaStreamSynchronize(c->s_compute));
 #undef LV_PIPE
     return LV_OK;
 }

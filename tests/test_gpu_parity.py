@@ -292,6 +292,41 @@ def test_host_step_equals_device_step(lv, orc, torch_cuda):
     ctx.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("ns,nf,chunk_mb", [(1, 30, None), (3, 4, "64"), (4, 9, "4")])
+def test_host_step_small_outputs_whole_step_staging(lv, orc, torch_cuda, monkeypatch, ns, nf, chunk_mb):
+    """The macroblock counts / map / summaries of a host step are staged for the whole step on the device and downloaded
+    once: a single stream cut into several chunks and a chunk that holds every frame of its streams write straight into
+    that staging, any other chunk shape is placed by k_place_small.  All three against the oracle, twice in a row (the
+    second call reuses the staging and carries the state)."""
+    if chunk_mb:
+        monkeypatch.setenv("LV_HOST_CHUNK_MB", chunk_mb)
+    w, h = 1280, 720
+    frames = orc.gen_batch("camera", 23, ns, 2 * nf, w, h)
+    prev = np.zeros((ns, w * h), np.uint8)
+    ctx = lv.Context(w, h, ns, 20, 0)
+    n = ns * nf
+    for half in range(2):
+        part = np.ascontiguousarray(frames[:, half * nf:(half + 1) * nf])
+        ref = orc.convert_diff_batch(part, prev, ns, nf, w, h, 20, 0, n_threads=4)
+        bgr = np.zeros(n * ctx.bgr_bytes, np.uint8)
+        cnt = np.zeros(n * ctx.mbs, np.uint16)
+        mp = np.full(n * ctx.mbs, 7, np.uint8)
+        summ = np.zeros(2 * n, np.uint32)
+        ctx.step_host(part.reshape(-1), ns, nf, bgr=bgr, mb_count=cnt, mb_map=mp, summary=summ)
+        assert np.array_equal(bgr, ref["bgr"])
+        assert np.array_equal(cnt, ref["mb_count"]) and np.array_equal(mp, ref["mb_map"])
+        assert np.array_equal(summ.reshape(-1, 2), ref["summary"])
+        # only one of the small outputs asked for
+        if half == 0:
+            ctx2 = lv.Context(w, h, ns, 20, 0)
+            mp2 = np.zeros(n * ctx.mbs, np.uint8)
+            ctx2.step_host(part.reshape(-1), ns, nf, mb_map=mp2)
+            assert np.array_equal(mp2, ref["mb_map"])
+            ctx2.close()
+    ctx.close()
+
+
 def test_device_generator_matches_oracle_generator(lv, orc, torch_cuda):
     for kind in ("uniform", "camera"):
         d = lv.gen_synthetic(kind, 1, 2, 5, 2, 3, 352, 288)
