@@ -218,10 +218,16 @@ __global__ void __launch_bounds__(256, kPic ? 4 : LV_TILE_MINBLOCKS) k_tile(cons
             y1 = ld16(yf + off + w);
         }
         [[maybe_unused]] uint2 u_early = make_uint2(0, 0), v_early = make_uint2(0, 0);
-        if constexpr (kEarly && kConv && !kPic) {
-            const uint32_t coff = (uint32_t)(row0 >> 1) * (uint32_t)(w >> 1) + (uint32_t)unit * 8u;
-            u_early = ld8_stream(yf + g.px + coff);
-            v_early = ld8_stream(yf + g.px + (g.px >> 2) + coff);
+        if constexpr (kEarly && kConv) {
+            if constexpr (kPic) {
+                const uint32_t pcoff = a.pic_c_off + (uint32_t)(row0 >> 1) * (uint32_t)(a.size_x >> 1) + (uint32_t)unit * 8u;
+                u_early = narrow8(pf + pcoff);
+                v_early = narrow8(pf + pcoff + a.pic_c_plane);
+            } else {
+                const uint32_t coff = (uint32_t)(row0 >> 1) * (uint32_t)(w >> 1) + (uint32_t)unit * 8u;
+                u_early = ld8_stream(yf + g.px + coff);
+                v_early = ld8_stream(yf + g.px + (g.px >> 2) + coff);
+            }
         }
 
         if constexpr (kDiff) {
@@ -269,13 +275,13 @@ __global__ void __launch_bounds__(256, kPic ? 4 : LV_TILE_MINBLOCKS) k_tile(cons
 
         if constexpr (kConv) {
             uint2 u, v;
-            if constexpr (kPic) {
+            if constexpr (kEarly) {
+                u = u_early;
+                v = v_early;
+            } else if constexpr (kPic) {
                 const uint32_t pcoff = a.pic_c_off + (uint32_t)(row0 >> 1) * (uint32_t)(a.size_x >> 1) + (uint32_t)unit * 8u;
                 u = narrow8(pf + pcoff);
                 v = narrow8(pf + pcoff + a.pic_c_plane);
-            } else if constexpr (kEarly) {
-                u = u_early;
-                v = v_early;
             } else {
                 const uint8_t *uf = yf + g.px;
                 const uint32_t coff = (uint32_t)(row0 >> 1) * (uint32_t)(w >> 1) + (uint32_t)unit * 8u;
@@ -429,22 +435,30 @@ __global__ void k_step_init(uint32_t *summary, int n_summary_words, const int4 *
     }
 }
 
-// ---- order of the six loads of the plain fused kernel --------------------------------------------------------------------
+// ---- order of the six loads of the fused kernels --------------------------------------------------------------------------
 // Measured on three B200 boards (profiles/r02_ab_kernel_variants.txt, "load order"): chroma loads issued early are 1.5 % faster
 // at 1080p and 1.7 - 2 % at 720p on every board; at 4K the same order is bimodal (213 us or 235 - 245 us from one round of 30
 // launches to the next, against a steady 218 - 220 us for the late order).  So the rule is static and by row length; a run-time
 // tuner that timed both instantiations on the caller's first launches was built and dropped (the 4K bimodality defeats a
 // handful of samples).  lv_set_kernel_variant(2 / 3) or LV_LOAD_ORDER=0 / 1 force one order (tests, A/B runs).
-int launch_fused_plain(const KArgs &a, int total_frames, cudaStream_t st)
+bool early_order(const KArgs &a)
 {
     static const int forced = [] {
         const char *s = getenv("LV_LOAD_ORDER");
         return (s && (s[0] == '0' || s[0] == '1') && !s[1]) ? s[0] - '0' : -1;
     }();
     const int var = kernel_variant();
-    const bool early = var >= 2 ? var == 3 : forced >= 0 ? forced == 1 : a.g.w <= 2048;
-    return early ? launch_tile_t<true, true, false, false, false, true>(a, total_frames, st)
-                 : launch_tile_t<true, true, false>(a, total_frames, st);
+    return var >= 2 ? var == 3 : forced >= 0 ? forced == 1 : a.g.w <= 2048;
+}
+
+// Fused instantiations that come in both orders: the plain step and the step from decoder pictures (1080p x 64: 113.2 -> 111.2 us
+// and 150.0 -> 142.1 us with the early order).  The mask and box instantiations keep the late order: early costs them
+// registers they do not have (bit mask 117.7 -> 119.4 us, box 119.5 -> 127.6 us with spills).
+template <bool kPic>
+int launch_fused(const KArgs &a, int total_frames, cudaStream_t st)
+{
+    return early_order(a) ? launch_tile_t<true, true, false, false, kPic, true>(a, total_frames, st)
+                          : launch_tile_t<true, true, false, false, kPic, false>(a, total_frames, st);
 }
 
 template <bool kConv, bool kDiff>
@@ -455,12 +469,11 @@ int launch_tile(KArgs a, int total_frames, cudaStream_t st)
     a.nf_magic = a.n_frames > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)a.n_frames - 1) / (uint64_t)a.n_frames) : 0u;
     const bool mask = a.mask_bits || a.mask_bytes;
     if constexpr (kConv && kDiff) {
-        if (a.pic0) return mask ? launch_tile_t<true, true, true, false, true>(a, total_frames, st)
-                                : launch_tile_t<true, true, false, false, true>(a, total_frames, st);
+        if (a.pic0) return mask ? launch_tile_t<true, true, true, false, true>(a, total_frames, st) : launch_fused<true>(a, total_frames, st);
+        if (!a.boxes && !mask) return launch_fused<false>(a, total_frames, st);
     }
     if (kDiff && a.boxes) return launch_tile_t<kConv, kDiff, kDiff, kDiff>(a, total_frames, st);   // masks too, when asked
     if (kDiff && mask) return launch_tile_t<kConv, kDiff, kDiff>(a, total_frames, st);
-    if constexpr (kConv && kDiff) return launch_fused_plain(a, total_frames, st);
     return launch_tile_t<kConv, kDiff, false>(a, total_frames, st);
 }
 

@@ -289,15 +289,23 @@ def test_convert_diff_pictures_is_narrow_then_step(lv, orc, torch_cuda, sx, sy, 
         assert np.array_equal(out["mb_count"].cpu().numpy().view(np.uint16), ref["mb_count"]), call
         assert np.array_equal(out["mb_map"].cpu().numpy(), ref["mb_map"]), call
         assert np.array_equal(out["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2), ref["summary"]), call
-        # without the masks (the common instantiation)
-        ctx2 = lv.Context(w, h, ns)
-        for s in range(ns):
-            ctx2.set_prev_luma(s, prev_in[s])
-        out2 = ctx2.alloc_outputs(n)
-        ctx2.convert_diff_pictures(d_pic, sx, sy, cl, ct, ns, nf, out2)
-        torch.cuda.synchronize()
-        assert np.array_equal(out2["bgr"].cpu().numpy(), ref["bgr"]) and np.array_equal(out2["mb_count"].cpu().numpy().view(np.uint16), ref["mb_count"])
-        ctx2.close()
+        # without the masks (the common instantiation), with either order of its loads forced and the default rule
+        for variant in ("tile_late", "tile_early", "tile"):
+            lv.set_kernel_variant(variant)
+            try:
+                ctx2 = lv.Context(w, h, ns)
+                for s in range(ns):
+                    ctx2.set_prev_luma(s, prev_in[s])
+                out2 = ctx2.alloc_outputs(n)
+                ctx2.convert_diff_pictures(d_pic, sx, sy, cl, ct, ns, nf, out2)
+                torch.cuda.synchronize()
+                assert np.array_equal(out2["bgr"].cpu().numpy(), ref["bgr"]), variant
+                assert np.array_equal(out2["mb_count"].cpu().numpy().view(np.uint16), ref["mb_count"]), variant
+                assert np.array_equal(out2["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2), ref["summary"]), variant
+                assert np.array_equal(ctx2.get_prev_luma(0), frames[0, -1, :px]), variant
+                ctx2.close()
+            finally:
+                lv.set_kernel_variant("tile")
         prev = frames[:, -1, :px].copy()
         for s in range(ns):
             assert np.array_equal(ctx.get_prev_luma(s), prev[s]), (call, s)
