@@ -243,8 +243,13 @@ LV_API size_t lv_format_bytes(int kind, int width, int height, int output);
  * lib/JM/output.c:427-451 writes into the pinned input).  lv_host_alloc / lv_host_free hand out
  * pinned memory; lv_step_host splits the batch into chunks of `chunk_frames` frames per stream group
  * and overlaps the upload of chunk k+1 (copy stream) with the kernel of chunk k and the download of
- * chunk k-1.  Host pointers may also be ordinary pageable memory (slower: staged by the driver).
- * Outputs may be NULL.  Synchronous: returns when every output is in host memory. */
+ * chunk k-1.  The first chunks of a step are small (1, 2, 4 ... frames, at least 1 MiB of input) so that the download
+ * stream -- the bottleneck: 3 of the 4.5 bytes per pixel that cross the link -- starts after one small upload; the
+ * macroblock counts, the map and the summaries are staged for the whole step on the device and downloaded once, beside
+ * the last pictures.  Host pointers may also be ordinary pageable memory (slower: staged by the driver).
+ * Outputs may be NULL.  Synchronous: returns when every output is in host memory.
+ * Environment (read at every call): LV_HOST_CHUNK_MB = input MiB per chunk (default 16), LV_HOST_SLOT_MB = MiB of input
+ * one of the three device slots may hold (default 256), LV_HOST_RAMP=0 switches the small first chunks off. */
 /* The upload half on its own, for consumers that keep the BGR on the device: lv_upload_async copies n_frames_total
  * I420 frames from (pinned) host memory into the context's device input slot `slot` (0 or 1, sized on demand) on the
  * context's copy stream and returns the device pointer; lv_upload_wait makes `cuda_stream` wait for that slot's copy.
