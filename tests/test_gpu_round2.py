@@ -17,6 +17,8 @@ import time
 import numpy as np
 import pytest
 
+from test_gpu_parity import assert_matches_oracle, run_fused
+
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -559,3 +561,57 @@ def test_exchange_dead_peer_gives_up_once(lv, torch_cuda):
     assert time.perf_counter() - t0 < 0.5                     # a broken exchange fails fast
     for x in xs:
         x.close()
+
+# ---- randomized sweep ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_randomized_geometry_batch_and_threshold_sweep(lv, orc, torch_cuda, seed, monkeypatch):
+    """Seeded random cases through the C ABI against the oracle: width a multiple of 16 (16 ... 2304, so both macroblock
+    mappings, rows longer and shorter than the early-load-order rule's 2048 pixels, partial last macroblock rows and ragged last
+    x tiles), even height, 1 - 5 streams x 1 - 6 frames, tol in 0 ... 255, mb_thresh in 0 ... 256, content with many
+    differences at exactly tol and tol + 1; two steps in a row (state carry), the second one through lv_step_host with a
+    random chunk size; masks on and off."""
+    torch = torch_cuda
+    rng = np.random.default_rng(1000 + seed)
+    w = 16 * int(rng.integers(1, 145))
+    h = 2 * int(rng.integers(1, 1 + max(1, min(300, 600000 // w) // 2)))
+    ns, nf = int(rng.integers(1, 6)), int(rng.integers(1, 7))
+    tol = int(rng.choice([0, 1, 7, 20, 25, 127, 128, 200, 254, 255]))
+    thr = int(rng.choice([0, 0, 1, 17, 128, 255, 256]))
+    px = w * h
+    monkeypatch.setenv("LV_HOST_CHUNK_MB", str(int(rng.choice([1, 2, 16]))))
+
+    def make(prev_luma):
+        fr = rng.integers(0, 256, (ns, nf, px * 3 // 2), dtype=np.uint8)
+        # luma of frame t = reference +- {tol, tol + 1, 0, random}: the compare's boundary is hit on a quarter of all pixels
+        ref_y = prev_luma
+        for t in range(nf):
+            kind = rng.integers(0, 4, (ns, px))
+            sign = rng.integers(0, 2, (ns, px)) * 2 - 1
+            d = np.where(kind == 0, tol, np.where(kind == 1, tol + 1, 0)) * sign
+            y = np.clip(ref_y.astype(np.int32) + d, 0, 255).astype(np.uint8)
+            y = np.where(kind == 3, fr[:, t, :px], y)
+            fr[:, t, :px] = y
+            ref_y = y
+        return fr
+
+    prev = np.zeros((ns, px), np.uint8)
+    ctx = lv.Context(w, h, ns, tol, thr)
+    masks = bool(seed & 1)
+    # step 1: device entry
+    frames = make(prev)
+    ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, tol, thr, want_mask=True)       # advances prev in place
+    got = run_fused(lv, torch, frames, ns, nf, w, h, tol, thr, ctx=ctx, masks=masks)
+    assert_matches_oracle(orc, got, ref, w, h, ns * nf, masks=masks)
+    # step 2: host entry on the same context (state carried on the device)
+    frames = make(prev)
+    ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, tol, thr)
+    n = ns * nf
+    bgr, cnt = np.zeros(n * ctx.bgr_bytes, np.uint8), np.zeros(n * ctx.mbs, np.uint16)
+    mp, summ = np.zeros(n * ctx.mbs, np.uint8), np.zeros(2 * n, np.uint32)
+    ctx.step_host(np.ascontiguousarray(frames.reshape(-1)), ns, nf, bgr=bgr, mb_count=cnt, mb_map=mp, summary=summ)
+    assert np.array_equal(bgr, ref["bgr"]), (w, h, ns, nf)
+    assert np.array_equal(cnt, ref["mb_count"]) and np.array_equal(mp, ref["mb_map"]), (w, h, ns, nf, tol, thr)
+    assert np.array_equal(summ.reshape(-1, 2), ref["summary"])
+    for s_ in range(ns):
+        assert np.array_equal(ctx.get_prev_luma(s_), prev[s_])
+    ctx.close()
