@@ -411,7 +411,8 @@ int launch_tile_t(const KArgs &a, int total_frames, cudaStream_t st)
         // ... and the row tiling would leave more than a tenth of the lanes idle (A/B on B200: 720p 401 -> 384 us; 1080p
         // and 4K, 94 % busy either way, are within 1 % and keep the row tiling whose warps never straddle two rows)
         const unsigned tiled_lanes = 32u * ((a.g.units + 31) / 32);
-        if (LV_TILE_FLAT && a.g.units == a.g.mb_w && mbs * mbw < (1ULL << 32) && 10u * a.g.units < 9u * tiled_lanes) {
+        // (mb_w == 1 has no 32-bit reciprocal -- ceil(2^32 / 1) -- and needs none: its row tiling is the same mapping)
+        if (LV_TILE_FLAT && a.g.units == a.g.mb_w && mbw >= 2 && mbs * mbw < (1ULL << 32) && 10u * a.g.units < 9u * tiled_lanes) {
             b.mbw_magic = (uint32_t)(((1ULL << 32) + mbw - 1) / mbw);
             grid = dim3((unsigned)((mbs + 31) / 32), 1, nf);
         }

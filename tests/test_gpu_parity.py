@@ -440,7 +440,7 @@ def test_kernel_variants_are_bit_identical(lv, orc, torch_cuda, variant):
     try:
         assert lv.get_kernel_variant() == variant
         for (w, h, ns, nf) in [(1920, 1080, 1, 3), (352, 288, 2, 3), (1280, 720, 3, 2), (96, 20, 2, 2), (64, 18, 1, 3),
-                               (4096, 24, 1, 2), (160, 8, 2, 2), (48, 18, 1, 2)]:
+                               (4096, 24, 1, 2), (160, 8, 2, 2), (48, 18, 1, 2), (16, 216, 2, 2), (32, 40, 1, 3)]:       # 16 x 216: one macroblock per row
             frames = orc.gen_batch("camera" if min(w, h) >= 16 else "uniform", 5, ns, nf, w, h)
             prev = np.zeros((ns, w * h), np.uint8)
             ref = orc.convert_diff_batch(frames, prev, ns, nf, w, h, 20, 0)

@@ -563,7 +563,7 @@ def test_exchange_dead_peer_gives_up_once(lv, torch_cuda):
         x.close()
 
 # ---- randomized sweep ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("seed", list(range(12)))
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("LV_SWEEP_SEEDS", "12")))))
 def test_randomized_geometry_batch_and_threshold_sweep(lv, orc, torch_cuda, seed, monkeypatch):
     """Seeded random cases through the C ABI against the oracle: width a multiple of 16 (16 ... 2304, so both macroblock
     mappings, rows longer and shorter than the early-load-order rule's 2048 pixels, partial last macroblock rows and ragged last
