@@ -470,7 +470,10 @@ def test_kernel_variants_are_bit_identical(lv, orc, torch_cuda, variant):
 def _full_size(lv, orc, torch, w, h, ns, nf, kind="camera"):
     n = ns * nf
     ctx = lv.Context(w, h, ns, 20, 0)
-    d_in = lv.gen_synthetic(kind, 1, 0, 0, ns, nf, w, h)
+    if min(w, h) >= 16:
+        d_in = lv.gen_synthetic(kind, 1, 0, 0, ns, nf, w, h)
+    else:                                   # the device generator works on whole macroblocks: generate on the host
+        d_in = torch.from_numpy(orc.gen_batch("uniform", 1, ns, nf, w, h).reshape(-1)).cuda()
     out = ctx.alloc_outputs(n, mask_bits=True)
     ctx.convert_diff_batch(d_in, ns, nf, out)
     torch.cuda.synchronize()
@@ -503,6 +506,14 @@ def test_config2_1080p_batch64(lv, orc, torch_cuda):
 
 def test_config3_4k_batch32(lv, orc, torch_cuda):
     _full_size(lv, orc, torch_cuda, 3840, 2160, 1, 32)
+
+
+@pytest.mark.parametrize("w,h,ns,nf", [(7680, 4320, 1, 3), (16384, 8192, 1, 2), (65536, 2, 2, 3), (16, 32768, 1, 2),
+                                        (32768, 16, 3, 2), (2048, 2048, 1, 5), (2064, 1038, 2, 3)])
+def test_extreme_geometries_full_outputs(lv, orc, torch_cuda, w, h, ns, nf):
+    """8K, a 128-megapixel picture, one row pair of 65 536 pixels, a 16-pixel column of 32 768 rows, the two sides of the
+    2 048-pixel load-order rule: every output against the oracle plus the size-independent properties."""
+    _full_size(lv, orc, torch_cuda, w, h, ns, nf, kind="camera" if min(w, h) >= 64 else "uniform")
 
 
 def test_config4_one_gpu_share_of_256_720p_streams(lv, orc, torch_cuda):
