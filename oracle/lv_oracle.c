@@ -92,8 +92,8 @@ LVO_HOT void lvo_yv12_to_rgb24(const uint8_t *src_y, const uint8_t *src_u, const
 {
     lvo_init_tables();
     const uint8_t *py1 = src_y, *py2 = src_y + width;
-    uint8_t *d1 = dst + 3 * width * (height - 1);   /* .text+0x350..0x39f */
-    uint8_t *d2 = d1 - 3 * width;
+    uint8_t *d1 = dst + (size_t)3 * width * (height - 1);   /* .text+0x350..0x39f; size_t: 2^30-pixel pictures pass 2^31 bytes */
+    uint8_t *d2 = d1 - (size_t)3 * width;
     const int back = (9 * width) & ~3;              /* .text+0x3a5..0x3b8 */
     for (int j = (height + 1) >> 1; j > 0; j--) {
         for (int i = (width + 3) >> 2; i > 0; i--) {

@@ -516,6 +516,17 @@ def test_extreme_geometries_full_outputs(lv, orc, torch_cuda, w, h, ns, nf):
     _full_size(lv, orc, torch_cuda, w, h, ns, nf, kind="camera" if min(w, h) >= 64 else "uniform")
 
 
+def test_largest_picture_the_api_accepts(lv, orc, torch_cuda):
+    """2^30 pixels (32 768 x 32 768), the largest picture lv_create takes: the kernel's 32-bit in-frame offsets reach 3 * 2^30 in
+    the BGR plane.  One frame, every output against the oracle; one pixel more is refused."""
+    import psutil
+    if psutil.virtual_memory().available < 24 << 30:
+        pytest.skip("needs ~16 GB of host memory for the picture, its BGR copy and the oracle's")
+    with pytest.raises(lv.LiveVideoError):
+        lv.Context(32768 + 16, 32768)
+    _full_size(lv, orc, torch_cuda, 32768, 32768, 1, 1)
+
+
 def test_config4_one_gpu_share_of_256_720p_streams(lv, orc, torch_cuda):
     # the 8-GPU share of config 4: 32 streams x 16 frames of 720p in one launch
     _full_size(lv, orc, torch_cuda, 1280, 720, 32, 16)
