@@ -527,6 +527,15 @@ def test_largest_picture_the_api_accepts(lv, orc, torch_cuda):
     _full_size(lv, orc, torch_cuda, 32768, 32768, 1, 1)
 
 
+def test_batch_whose_outputs_pass_4_gib(lv, orc, torch_cuda):
+    """180 frames of 4K in one launch: the BGR batch is 4.48 GB, so the last frames sit beyond 2^32 bytes (the kernel's 64-bit
+    frame bases + 32-bit in-frame offsets); every output against the oracle."""
+    import psutil
+    if psutil.virtual_memory().available < 32 << 30:
+        pytest.skip("needs ~16 GB of host memory")
+    _full_size(lv, orc, torch_cuda, 3840, 2160, 3, 60)
+
+
 def test_config4_one_gpu_share_of_256_720p_streams(lv, orc, torch_cuda):
     # the 8-GPU share of config 4: 32 streams x 16 frames of 720p in one launch
     _full_size(lv, orc, torch_cuda, 1280, 720, 32, 16)
