@@ -266,6 +266,12 @@ LV_API int lv_host_free(void *p);
  * by DMA instead of through the driver's pageable staging.  Keep the range allocated until lv_host_unregister. */
 LV_API int lv_host_register(void *p, size_t bytes);
 LV_API int lv_host_unregister(void *p);
+/* How lv_step_host / lv_step_host_pictures would cut a step of n_streams x n_frames frames into chunks under the current
+ * environment, without touching a device (pure host logic; the CPU tests walk it): returns the number of chunks and stores
+ * up to max_chunks of them as {first stream, streams, first frame, frames} in chunks4.  in_frame_bytes = host bytes per
+ * frame (0: I420, width * height * 3 / 2; decoder pictures: 2 bytes per sample). */
+LV_API int lv_host_step_plan(int width, int height, size_t in_frame_bytes, int n_streams, int n_frames, int *chunks4,
+                             int max_chunks);
 LV_API int lv_step_host(lv_ctx *ctx, const uint8_t *h_i420, int first_stream, int n_streams, int n_frames,
                         uint8_t *h_bgr, uint16_t *h_mask_bits, uint16_t *h_mb_count, uint8_t *h_mb_map,
                         uint32_t *h_summary);

@@ -525,6 +525,18 @@ def get_zero_copy():
     return {n: k for k, n in ZERO_COPY_MODES.items()}[v]
 
 
+def host_step_plan(width, height, n_streams, n_frames, in_frame_bytes=0):
+    """lv_host_step_plan: the chunks (first stream, streams, first frame, frames) a host step would be cut into under the
+    current environment (LV_HOST_CHUNK_MB, LV_HOST_SLOT_MB, LV_HOST_RAMP); no device is touched."""
+    L = capi.lib()
+    n = L.lv_host_step_plan(width, height, in_frame_bytes, n_streams, n_frames, None, 0)
+    capi.check(min(n, 0), "lv_host_step_plan")
+    buf = (C.c_int * (4 * max(n, 1)))()
+    n2 = L.lv_host_step_plan(width, height, in_frame_bytes, n_streams, n_frames, C.cast(buf, C.c_void_p), n)
+    assert n2 == n
+    return [tuple(buf[4 * i:4 * i + 4]) for i in range(n)]
+
+
 def gen_synthetic(kind, seed, first_stream, first_frame, n_streams, n_frames, width, height, out=None, device=0,
                   cuda_stream=None):
     """Synthetic I420 frames on the device (`uniform` or `camera` generator)."""

@@ -759,6 +759,54 @@ struct PicSource {
     size_t samples;              // per picture
 };
 
+// ---- how a host step is cut into chunks (pure host logic: lv_host_step_plan exposes it, the CPU tests walk it) ----------
+// chunk = `nt` consecutive frames of `ns` consecutive streams.  Sizes: ~LV_HOST_CHUNK_MB MiB of input per chunk, at least one
+// frame; a device slot holds at most LV_HOST_SLOT_MB MiB of I420 input (default 256), so when one frame of all streams is
+// larger the streams are cut too (streams keep their state independently: a cut by streams costs nothing).  The first chunks
+// of a step ramp up (1, 2, 4 ... frames, at least 1 MiB of input): nothing can be downloaded before the first chunk has been
+// uploaded and computed, so the pipeline is filled with a small one.
+struct HostChunk {
+    int s0, ns, t0, nt;
+};
+struct HostPlan {
+    int cs = 0, cf = 0;              // largest chunk: streams x frames (what a slot must hold)
+    std::vector<HostChunk> chunks;
+};
+HostPlan plan_host_step(size_t in_frame, size_t dev_frame, int n_streams, int n_frames)
+{
+    auto env_mb = [](const char *name, long dflt, long max) -> size_t {
+        const char *e = getenv(name);
+        const long mb = e ? atol(e) : 0;
+        return (size_t)(mb > 0 && mb <= max ? mb : dflt) << 20;
+    };
+    HostPlan p;
+    if (n_streams <= 0 || n_frames <= 0 || !in_frame || !dev_frame) return p;
+    const size_t chunk_bytes = env_mb("LV_HOST_CHUNK_MB", LV_HOST_CHUNK_MB_DEFAULT, 1024);
+    int cf = (int)(chunk_bytes / (in_frame * (size_t)n_streams));
+    if (cf < 1) cf = 1;
+    if (cf > n_frames) cf = n_frames;
+    int cs = n_streams;
+    const size_t slot_bytes = env_mb("LV_HOST_SLOT_MB", 256, 16384);
+    const size_t cap_frames = slot_bytes / dev_frame > 0 ? slot_bytes / dev_frame : 1;
+    if ((size_t)cs * cf > cap_frames) { cf = 1; if ((size_t)cs > cap_frames) cs = (int)cap_frames; }
+    p.cs = cs; p.cf = cf;
+    const char *ramp_env = getenv("LV_HOST_RAMP");
+    const bool ramp_on = !(ramp_env && ramp_env[0] == '0');
+    const size_t ramp_in = in_frame * (size_t)cs;                       // input bytes of one frame of every stream in a chunk
+    const int ramp0 = ramp_in >= ((size_t)1 << 20) ? 1 : (int)((((size_t)1 << 20) + ramp_in - 1) / ramp_in);   // >= 1 MiB
+    for (int s0 = 0; s0 < n_streams; s0 += cs) {
+        const int ns = n_streams - s0 < cs ? n_streams - s0 : cs;
+        int ramp = s0 == 0 && ramp_on ? ramp0 : cf;                     // later stream groups find the pipeline full
+        for (int t0 = 0, nt = 0; t0 < n_frames; t0 += nt) {
+            nt = ramp < cf ? ramp : cf;
+            if (nt > n_frames - t0) nt = n_frames - t0;
+            ramp = ramp < cf ? ramp * 2 : cf;
+            p.chunks.push_back(HostChunk{s0, ns, t0, nt});
+        }
+    }
+    return p;
+}
+
 int ensure_pic_slots(lv_ctx *c, size_t samples)
 {
     if (c->pic_cap >= samples) return LV_OK;
@@ -783,23 +831,9 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
     const lv::Geom &g = c->g;
     const size_t mbs = (size_t)g.mb_w * g.mb_h, units = (size_t)g.units * g.h;
 
-    // chunk = cf frames of every stream; aim at ~LV_HOST_CHUNK_MB MiB of input per chunk, at least 1 frame
-    auto env_mb = [](const char *name, long dflt, long max) -> size_t {
-        const char *e = getenv(name);
-        const long mb = e ? atol(e) : 0;
-        return (size_t)(mb > 0 && mb <= max ? mb : dflt) << 20;
-    };
-    const size_t chunk_bytes = env_mb("LV_HOST_CHUNK_MB", LV_HOST_CHUNK_MB_DEFAULT, 1024);
     const size_t in_frame = pic ? pic->samples * sizeof(uint16_t) : g.frame;     // host bytes per frame
-    int cf = (int)(chunk_bytes / (in_frame * (size_t)n_streams));
-    if (cf < 1) cf = 1;
-    if (cf > n_frames) cf = n_frames;
-    // a slot must hold one chunk (at most LV_HOST_SLOT_MB MiB of input, default 256): streams are cut too when even one
-    // frame of all streams is larger.  Streams keep their state independently, so a cut by streams costs nothing.
-    int cs = n_streams;
-    const size_t slot_bytes = env_mb("LV_HOST_SLOT_MB", 256, 16384);
-    const size_t cap_frames = slot_bytes / g.frame > 0 ? slot_bytes / g.frame : 1;
-    if ((size_t)cs * cf > cap_frames) { cf = 1; if ((size_t)cs > cap_frames) cs = (int)cap_frames; }
+    const HostPlan plan = plan_host_step(in_frame, g.frame, n_streams, n_frames);
+    const int cs = plan.cs, cf = plan.cf;
     int rc = ensure_pipeline(c, cs * cf);
     if (rc != LV_OK) return rc;
     if (pic) {
@@ -843,19 +877,9 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
     } while (0)
 
     int k = 0;
-    const char *ramp_env = getenv("LV_HOST_RAMP");
-    const bool ramp_on = !(ramp_env && ramp_env[0] == '0');
-    const size_t ramp_in = in_frame * (size_t)cs;                       // input bytes of one frame of every stream in a chunk
-    const int ramp0 = ramp_in >= ((size_t)1 << 20) ? 1 : (int)((((size_t)1 << 20) + ramp_in - 1) / ramp_in);   // >= 1 MiB
-    for (int s0 = 0; s0 < n_streams; s0 += cs) {
-        const int ns = n_streams - s0 < cs ? n_streams - s0 : cs;
-        // the first chunks of a step ramp up (1, 2, 4 ... frames, at least 1 MiB of input): nothing can be downloaded
-        // before the first chunk has been uploaded and computed, so the pipeline is filled with a small one
-        int ramp = s0 == 0 && ramp_on ? ramp0 : cf;
-        for (int t0 = 0, nt = 0; t0 < n_frames; t0 += nt, k++) {
-            nt = ramp < cf ? ramp : cf;
-            if (nt > n_frames - t0) nt = n_frames - t0;
-            ramp = ramp < cf ? ramp * 2 : cf;
+    for (const HostChunk &ch : plan.chunks) {
+        {
+            const int s0 = ch.s0, ns = ch.ns, t0 = ch.t0, nt = ch.nt;
             const int slot = k % lv_ctx::kSlots;
             // the slot's previous download must have drained before its buffers are reused
             if (k >= lv_ctx::kSlots) {
@@ -912,6 +936,7 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
             if (h_bgr) LV_PIPE(down(h_bgr, c->d_bgr[slot], 3 * g.px));
             if (h_mask_bits) LV_PIPE(down(h_mask_bits, c->d_bits[slot], sizeof(uint16_t) * units));
             LV_PIPE(cudaEventRecord(c->ev_out[slot], c->s_copy_out));
+            k++;
         }
     }
     // the small outputs of the whole step: one copy per array, on the upload stream (idle by now), beside the last
@@ -931,6 +956,21 @@ int step_host_impl(lv_ctx *c, const uint8_t *h_i420, const PicSource *pic, int f
     return LV_OK;
 }
 }  // namespace
+
+int lv_host_step_plan(int width, int height, size_t in_frame_bytes, int n_streams, int n_frames, int *chunks4, int max_chunks)
+{
+    if (width < 4 || height < 2 || width % 4 != 0 || height % 2 != 0 || n_streams < 0 || n_frames < 0 || max_chunks < 0 ||
+        (max_chunks > 0 && !chunks4))
+        return LV_E_ARG;
+    const size_t frame = (size_t)width * height * 3 / 2;
+    const HostPlan p = plan_host_step(in_frame_bytes ? in_frame_bytes : frame, frame, n_streams, n_frames);
+    const int n = (int)p.chunks.size();
+    for (int i = 0; i < n && i < max_chunks; i++) {
+        chunks4[4 * i] = p.chunks[i].s0; chunks4[4 * i + 1] = p.chunks[i].ns;
+        chunks4[4 * i + 2] = p.chunks[i].t0; chunks4[4 * i + 3] = p.chunks[i].nt;
+    }
+    return n;
+}
 
 int lv_step_host(lv_ctx *c, const uint8_t *h_i420, int first_stream, int n_streams, int n_frames, uint8_t *h_bgr,
                  uint16_t *h_mask_bits, uint16_t *h_mb_count, uint8_t *h_mb_map, uint32_t *h_summary)
