@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 JM = os.path.join(ROOT, "oracle", "_ref", "jm_ldecod")
+JM_INPROC = os.path.join(ROOT, "oracle", "_ref", "jm_inproc")
 
 
 def run(width, height, n_frames, batch, check=True, seed=1):
@@ -108,6 +109,7 @@ def run(width, height, n_frames, batch, check=True, seed=1):
     t_dec = time.perf_counter() - t0
 
     ok = None
+    ref = None
     if check:
         frames = np.stack([orc.gen("camera", seed, 0, t, width, height) for t in range(n_frames)])[None]
         assert np.array_equal(first_batch_in, frames[0, :sizes[0]].reshape(-1)), "JM output != generator frames"
@@ -132,6 +134,36 @@ def run(width, height, n_frames, batch, check=True, seed=1):
         "gpu_launches": ctx.kernel_launches,
     }
     ctx.close()
+    # second feed: the decoder and the GPU library in ONE process (oracle/_ref/jm_inproc: JM unmodified, its write_out_picture
+    # replaced at link time; the real unsigned-short planes go to lv_step_host_pictures, narrowed and cropped on the device)
+    if os.path.exists(JM_INPROC):
+        prefix = os.path.join(tmp, "inproc")
+        t0 = time.perf_counter()
+        r = subprocess.run([JM_INPROC, stream, str(width), str(height), str(batch), prefix], capture_output=True, timeout=900)
+        t_in = time.perf_counter() - t0
+        if r.returncode == 0:
+            ip = json.loads(r.stdout.decode().strip().splitlines()[-1])
+            ok2 = None
+            if check:
+                ok2 = bool(np.array_equal(np.fromfile(prefix + ".bgr", np.uint8), ref["bgr"]) and
+                           np.array_equal(np.fromfile(prefix + ".cnt", np.uint16), ref["mb_count"]) and
+                           np.array_equal(np.fromfile(prefix + ".map", np.uint8), ref["mb_map"]) and
+                           np.array_equal(np.fromfile(prefix + ".sum", np.uint32).reshape(-1, 2), ref["summary"]))
+            rep["in_process"] = {
+                "what": "jm_inproc: decoder + liblivevideo.so in one process, 16-bit decoder pictures -> lv_step_host_pictures "
+                        "(synchronous per batch: decode and GPU stage alternate)",
+                "e2e_fps": ip["frames"] / ip["total_s"], "gpu_stage_s": ip["gpu_stage_s"], "plane_copy_s": ip["plane_copy_s"],
+                "gpu_stage_mpx_s": px / ip["gpu_stage_s"] / 1e6 if ip["gpu_stage_s"] > 0 else None,
+                "gpu_stage_fraction_of_wall": ip["gpu_stage_s"] / ip["total_s"], "picture": ip["picture"],
+                "imgpel_bytes": ip["imgpel_bytes"], "gpu_launches": ip["gpu_launches"], "process_wall_s": t_in,
+                "bit_exact_vs_oracle": ok2}
+        else:
+            rep["in_process"] = {"error": r.stderr.decode()[-300:]}
+        for ext in ("bgr", "cnt", "map", "sum"):
+            try:
+                os.remove(prefix + "." + ext)
+            except OSError:
+                pass
     try:
         os.remove(stream)
         os.rmdir(tmp)

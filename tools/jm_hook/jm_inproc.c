@@ -17,10 +17,14 @@
  * one JSON line with the timings goes to stdout.  A maintainer's binding in the application is the same function
  * (INTEGRATION.md).
  */
+#include <pthread.h>
+#include <stdio_ext.h>
 #include <time.h>
 
 #include "jm_driver.h"          /* oracle/jm: the decoder driver (reference headers) */
 #include "livevideo.h"
+
+extern FILE *bits;              /* lib/JM/annexb.c:26 */
 
 static struct {
     lv_ctx *ctx;
@@ -37,6 +41,7 @@ static struct {
     size_t mbs, bgr_bytes;
     double gpu_s, copy_s;
     int failed;
+    int dry;                    /* JM_INPROC_DRY=1: no GPU at all (timing of the decoder inside this process) */
 } H;
 
 static double now_s(void)
@@ -59,6 +64,7 @@ static void hook_flush(void)
         H.sum = (uint32_t *)realloc(H.sum, H.cap * 2 * sizeof(uint32_t));
         if (!H.bgr || !H.cnt || !H.map || !H.sum) { H.failed = 1; return; }
     }
+    if (H.dry) { H.frames += (size_t)H.filled; H.filled = 0; return; }
     t0 = now_s();
     rc = lv_step_host_pictures(H.ctx, H.pics, H.size_x, H.size_y, H.crop_left, H.crop_top, 0, 1, H.filled,
                                H.bgr + H.frames * H.bgr_bytes, NULL, H.cnt + H.frames * H.mbs, H.map + H.frames * H.mbs,
@@ -106,7 +112,8 @@ void write_out_picture(StorablePicture *p, int p_out_unused)
             H.failed = 1;
             return;
         }
-        if (lv_host_alloc(&pin, (size_t)H.batch * H.samples * sizeof(uint16_t)) != LV_OK) { H.failed = 1; return; }
+        if (H.dry) pin = malloc((size_t)H.batch * H.samples * sizeof(uint16_t));
+        else if (lv_host_alloc(&pin, (size_t)H.batch * H.samples * sizeof(uint16_t)) != LV_OK) { H.failed = 1; return; }
         H.pics = (uint16_t *)pin;
     }
     if (p->size_x != H.size_x || p->size_y != H.size_y || crop_left != H.crop_left || crop_top != H.crop_top) {
@@ -135,6 +142,8 @@ static int dump(const char *prefix, const char *ext, const void *data, size_t by
     return fclose(f) != 0;
 }
 
+static void *idle_thread(void *a) { (void)a; for (;;) pause(); return NULL; }
+
 int main(int argc, char **argv)
 {
     double t0, t_total;
@@ -145,20 +154,32 @@ int main(int argc, char **argv)
     }
     H.width = atoi(argv[2]); H.height = atoi(argv[3]); H.batch = atoi(argv[4]);
     if (H.batch < 1) H.batch = 1;
-    rc = lv_create(0, H.width, H.height, 1, 20, 0, &H.ctx);
+    H.dry = getenv("JM_INPROC_DRY") != NULL;
+    if (getenv("JM_INPROC_THREAD")) { pthread_t t; pthread_create(&t, NULL, idle_thread, NULL); }
+    rc = H.dry ? LV_OK : lv_create(0, H.width, H.height, 1, 20, 0, &H.ctx);
     if (rc != LV_OK) {
         fprintf(stderr, "jm_inproc: lv_create: %s (%s)\n", lv_strerror(rc), lv_last_error());
         return 3;
     }
-    H.mbs = lv_frame_mbs(H.ctx);
-    H.bgr_bytes = lv_frame_bytes_bgr(H.ctx);
+    H.mbs = H.dry ? 1 : lv_frame_mbs(H.ctx);
+    H.bgr_bytes = H.dry ? 1 : lv_frame_bytes_bgr(H.ctx);
     rc = jmd_open(argv[1], "(in process)", -1, H.width, H.height);
     if (rc) return rc;
+    /* The decoder reads its stream one fgetc() at a time (feof + fgetc per byte, lib/JM/annexb.c:65-142: 400 million calls for 64 I_PCM pictures of 1080p).
+     * glibc skips the FILE lock while a process has a single thread; the CUDA runtime starts threads, and from then on every
+     * call locks: the decoder ran at 7.4 pictures/s in this process against 16 on its own.  Only this thread reads the
+     * stream, so take the lock out of the calls (the reference's source is untouched). */
+    __fsetlocking(bits, FSETLOCKING_BYCALLER);      /* GetAnnexbNALU (image.c:2263) */
+    __fsetlocking(bitss, FSETLOCKING_BYCALLER);     /* partial_GetAnnexbNALU (image.c:2626) */
     t0 = now_s();
     jmd_decode_all();
     hook_flush();                                   /* the last, partial batch */
     t_total = now_s() - t0;
     if (H.failed) return 6;
+    if (H.dry) {
+        printf("{\"frames\": %zu, \"total_s\": %.6f, \"plane_copy_s\": %.6f, \"dry\": true}\n", H.frames, t_total, H.copy_s);
+        return 0;
+    }
     if (dump(argv[5], "bgr", H.bgr, H.frames * H.bgr_bytes) || dump(argv[5], "cnt", H.cnt, H.frames * H.mbs * 2) ||
         dump(argv[5], "map", H.map, H.frames * H.mbs) || dump(argv[5], "sum", H.sum, H.frames * 8))
         return 7;
