@@ -288,3 +288,99 @@ def test_random_multi_picture_entries(lv, orc, torch_cuda, seed):
         if pinned:
             for a in ys + us + vs + ds:
                 lv.host_unregister(a)
+
+
+# ---- a random SESSION on one context: the per-stream state under every call that touches it ----------------------------
+@pytest.mark.parametrize("seed", SEEDS)
+def test_random_stateful_session(lv, orc, torch_cuda, seed):
+    """A context with several streams driven by a random sequence of calls -- device steps and host steps over random stream
+    ranges and frame counts, decoder-picture steps, tol / mb_thresh changes, the static-background mode switched on and off,
+    set / reset of a stream's previous luma -- against a host model that keeps one previous-luma plane per stream
+    (lib/JM/image.c:1553-1561; static mode: MainDlg.cpp:238-246).  After every call all outputs and every stream's state must
+    equal the model's."""
+    torch = torch_cuda
+    rng = np.random.default_rng(9000 + seed)
+    w, h = _geom16(rng, 60000)
+    S = int(rng.integers(1, 7))
+    px = w * h
+    tol, thr = 20, 0
+    ctx = lv.Context(w, h, S, tol, thr)
+    prev = np.zeros((S, px), np.uint8)
+    static = False
+
+    def model(frames, first, cnt, T):
+        """advance the model over streams [first, first + cnt) and return the expected outputs"""
+        if not static:
+            sub = prev[first:first + cnt].copy()
+            ref = orc.convert_diff_batch(frames, sub, cnt, T, w, h, tol, thr)
+            prev[first:first + cnt] = sub
+            return ref["bgr"], ref["mb_count"], ref["mb_map"], ref["summary"]
+        bgr, cnts, maps, summ = [], [], [], []
+        for s in range(cnt):
+            for t in range(T):
+                _, c, m, changed = orc.frame_diff_mb(frames[s, t, :px], prev[first + s], w, h, tol, thr)
+                bgr.append(orc.convert_frame(frames[s, t], w, h)), cnts.append(c), maps.append(m)
+                summ.append((changed, int(m.sum())))
+        return np.concatenate(bgr), np.concatenate(cnts), np.concatenate(maps), np.array(summ, np.uint32)
+
+    for step in range(int(rng.integers(6, 14))):
+        op = int(rng.integers(0, 10))
+        if op == 0:
+            tol, thr = int(rng.integers(0, 256)), int(rng.choice([0, 0, 2, 256]))
+            ctx.set_params(tol, thr)
+            continue
+        if op == 1:
+            static = not static
+            ctx.set_ref_mode(static)
+            continue
+        if op == 2:
+            s = int(rng.integers(0, S))
+            if rng.integers(0, 2):
+                y = rng.integers(0, 256, px, dtype=np.uint8)
+                ctx.set_prev_luma(s, y)
+                prev[s] = y
+            else:
+                ctx.reset_prev_luma()
+                prev[:] = 0
+            continue
+        first = int(rng.integers(0, S))
+        cnt = int(rng.integers(1, S - first + 1))
+        T = int(rng.integers(1, 5))
+        n = cnt * T
+        frames = rng.integers(0, 256, (cnt, T, px * 3 // 2), dtype=np.uint8)
+        # luma close to the model's reference so that differences straddle the tolerance
+        base = prev[first:first + cnt]
+        for t in range(T):
+            d = rng.choice([-tol - 1, -tol, 0, 0, tol, tol + 1], (cnt, px))
+            y = np.clip(base.astype(int) + d, 0, 255).astype(np.uint8)
+            frames[:, t, :px] = np.where(rng.random((cnt, px)) < 0.9, y, frames[:, t, :px])
+            if not static:
+                base = frames[:, t, :px]
+        if op <= 5:                                  # device step
+            want = model(frames, first, cnt, T)
+            out = ctx.alloc_outputs(n)
+            ctx.convert_diff_batch(torch.from_numpy(frames.reshape(-1)).cuda(), cnt, T, out, first_stream=first)
+            torch.cuda.synchronize()
+            got = (out["bgr"].cpu().numpy(), out["mb_count"].cpu().numpy().view(np.uint16), out["mb_map"].cpu().numpy(),
+                   out["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2))
+        elif op <= 7:                                # host step
+            want = model(frames, first, cnt, T)
+            bgr, c16 = np.zeros(n * ctx.bgr_bytes, np.uint8), np.zeros(n * ctx.mbs, np.uint16)
+            mp, summ = np.zeros(n * ctx.mbs, np.uint8), np.zeros(2 * n, np.uint32)
+            ctx.step_host(np.ascontiguousarray(frames.reshape(-1)), cnt, T, bgr=bgr, mb_count=c16, mb_map=mp, summary=summ,
+                          first_stream=first)
+            got = (bgr, c16, mp, summ.reshape(-1, 2))
+        else:                                        # decoder pictures (upper bytes random: they are dropped, not clipped)
+            want = model(frames, first, cnt, T)
+            pics = frames.astype(np.uint16) | (rng.integers(0, 256, frames.shape, dtype=np.uint16) << 8)
+            out = ctx.alloc_outputs(n)
+            ctx.convert_diff_pictures(torch.from_numpy(np.ascontiguousarray(pics).view(np.int16).reshape(-1)).cuda(), w, h, 0, 0,
+                                      cnt, T, out, first_stream=first)
+            torch.cuda.synchronize()
+            got = (out["bgr"].cpu().numpy(), out["mb_count"].cpu().numpy().view(np.uint16), out["mb_map"].cpu().numpy(),
+                   out["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2))
+        for name, g, e in zip(("bgr", "mb_count", "mb_map", "summary"), got, want):
+            assert np.array_equal(g, e), (seed, step, op, name, w, h, first, cnt, T, static, tol, thr)
+        for s in range(S):
+            assert np.array_equal(ctx.get_prev_luma(s), prev[s]), (seed, step, op, "state", s, static)
+    ctx.close()
