@@ -40,6 +40,8 @@ SYMBOLS = {
     "lv_convert_diff_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lv_convert_diff_batch_ex": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "lv_convert_diff_box_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
+    "lv_convert_diff_box_batch_ex": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp,
+                                               C.c_int]),
     "lv_object_windows": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "lv_object_update": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "lv_convert_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),

@@ -460,6 +460,7 @@ int step_impl(lv_ctx *c, const uint8_t *d_i420, int first_stream, int n_streams,
             a.windows = d_windows + 4 * f0 * n_objects;
             a.boxes = d_boxes + 4 * f0 * n_objects;
             a.n_obj = n_objects;
+            a.box_windowed = (flags & LV_BOX_WINDOWED) ? 1 : 0;
         }
         const int rc = launch_result(lv::launch_step(a, st), c->launches);
         if (rc != LV_OK) return rc;
@@ -489,6 +490,17 @@ int lv_convert_diff_box_batch(lv_ctx *c, const uint8_t *d_i420, int first_stream
     if (!aligned(d_windows, 16) || !aligned(d_boxes, 16)) return misaligned("d_windows / d_boxes (16 bytes)");
     return step_impl(c, d_i420, first_stream, n_streams, n_frames, d_bgr, nullptr, nullptr, d_mb_count, d_mb_map, d_summary,
                      d_windows, n_objects, d_boxes, cuda_stream, 0);
+}
+
+int lv_convert_diff_box_batch_ex(lv_ctx *c, const uint8_t *d_i420, int first_stream, int n_streams, int n_frames, uint8_t *d_bgr,
+                                 uint16_t *d_mb_count, uint8_t *d_mb_map, uint32_t *d_summary, const int *d_windows,
+                                 int n_objects, int *d_boxes, void *cuda_stream, int flags)
+{
+    if (!d_windows || !d_boxes || n_objects < 1 || n_objects > LV_MAX_OBJECTS) return LV_E_ARG;
+    if (flags & ~(LV_BOX_WINDOWED | LV_STEP_SUMMARY_PREZEROED)) return LV_E_ARG;
+    if (!aligned(d_windows, 16) || !aligned(d_boxes, 16)) return misaligned("d_windows / d_boxes (16 bytes)");
+    return step_impl(c, d_i420, first_stream, n_streams, n_frames, d_bgr, nullptr, nullptr, d_mb_count, d_mb_map, d_summary,
+                     d_windows, n_objects, d_boxes, cuda_stream, flags);
 }
 
 int lv_object_windows(lv_ctx *c, const int *d_objects, int n, int hor_margin, int ver_margin, int *d_windows, void *cuda_stream)

@@ -436,6 +436,109 @@ __global__ void k_step_init(uint32_t *summary, int n_summary_words, const int4 *
     }
 }
 
+// ---- the object boxes as a pass of their own over the WINDOWS only -----------------------------------------------------------
+// lv_convert_diff_box_batch_ex(LV_BOX_WINDOWED): the plain fused step (early load order, 111 us) followed by this kernel, which
+// re-reads current and reference luma inside each object's window (lib/JM/image.c:4818-4838) -- from L2 or HBM, a few KB per
+// window of the reference's size -- instead of carrying the mask and the box machinery through every block of the picture
+// (+8 us).  Measured (1080p x 64): 117.4 us against 119.4 us fused with one window per picture, 119.5 against 121.0 with four:
+// a small kernel behind the step costs ~5 us however little it does (dependent launch + two memory latencies), so the gain is
+// 2 us; a window as large as the picture costs a second, slow pass over the luma (340 us against 125): the fused form stays
+// the default.  grid = (slabs of the window's rows, objects, frames).
+constexpr int kBoxSlabs = 8, kBoxThreads = 64, kBoxInFlight = 8;     // small blocks: every block of a launch is resident at once
+__global__ void __launch_bounds__(kBoxThreads) k_box_windows(const KArgs a)
+{
+    const Geom &g = a.g;
+    const int f = a.f_base + blockIdx.z, k = blockIdx.y;
+    const int4 wd = __ldg(a.windows + (size_t)f * a.n_obj + k);                    // x0, x1, y0, y1, inclusive
+    const int x0 = wd.x < 0 ? 0 : wd.x, x1 = wd.y > g.w - 1 ? g.w - 1 : wd.y;
+    const int y0 = wd.z < 0 ? 0 : wd.z, y1 = wd.w > g.h - 1 ? g.h - 1 : wd.w;
+    if (x0 > x1 || y0 > y1) return;
+    const int ny = y1 - y0 + 1;
+    const int r0 = y0 + (int)(((long long)ny * blockIdx.x) / gridDim.x), r1 = y0 + (int)(((long long)ny * (blockIdx.x + 1)) / gridDim.x);
+    if (r0 >= r1) return;
+    const int s = a.n_frames == 1 ? f : (int)__umulhi((uint32_t)f, a.nf_magic);
+    const int t = f - s * a.n_frames;
+    const uint8_t *cur = a.y0 + (size_t)f * a.y_stride;
+    const uint8_t *ref = (t == 0 || a.static_ref) ? a.state_in + (size_t)s * g.px : cur - a.y_stride;
+    const uint32_t tol4 = (uint32_t)a.tol * 0x01010101u, ntol7 = ~tol4 & 0x7f7f7f7fu;
+    const int wa = x0 >> 2, nw = (x1 >> 2) - wa + 1;                               // 4-pixel words of a row
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int mnx = 0x7fffffff, mxx = -0x7fffffff, mny = 0x7fffffff, mxy = -0x7fffffff;
+    // the slab's words as one flat index space, eight per thread in flight: a window of the reference's size is a single
+    // memory latency per block.  i / nw by a multiply-high with ceil(2^32 / nw) is exact while total * nw < 2^32 (every window
+    // of a 4K picture); beyond that -- windows of pictures tens of thousands of pixels wide -- the plain division
+    const int total = nw * (r1 - r0);
+    const bool exact = (unsigned long long)total * (unsigned)nw < (1ULL << 32);
+    const uint32_t nw_magic = nw > 1 ? (uint32_t)((0x100000000ULL + (uint32_t)nw - 1) / (uint32_t)nw) : 0u;
+    for (int base = threadIdx.x; base < total; base += kBoxInFlight * kBoxThreads) {
+        uint32_t c[kBoxInFlight], p[kBoxInFlight];
+        int rr[kBoxInFlight], xa[kBoxInFlight];
+#pragma unroll
+        for (int u = 0; u < kBoxInFlight; u++) {
+            const int i = base + u * kBoxThreads;
+            c[u] = p[u] = 0u;
+            rr[u] = xa[u] = 0;
+            if (i < total) {
+                const int q = nw == 1 ? i : exact ? (int)__umulhi((uint32_t)i, nw_magic) : i / nw;
+                rr[u] = r0 + q;
+                xa[u] = (wa + (i - q * nw)) * 4;
+                const size_t o = (size_t)rr[u] * g.w + (size_t)xa[u];
+                c[u] = __ldg(reinterpret_cast<const uint32_t *>(cur + o));
+                p[u] = __ldg(reinterpret_cast<const uint32_t *>(ref + o));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBoxInFlight; u++) {
+            uint32_t m = diff_gt4(c[u], p[u], tol4, ntol7) & 0x80808080u;
+            if (base + u * kBoxThreads >= total) m = 0u;
+            if (xa[u] < x0) m &= 0xffffffffu << (8 * (x0 - xa[u]));                // pixels left of the window
+            if (xa[u] + 3 > x1) m &= 0xffffffffu >> (8 * (xa[u] + 3 - x1));        // pixels right of it
+            if (m) {
+                const int first = (__ffs((int)m) - 1) >> 3, last = (31 - __clz((int)m)) >> 3;
+                mnx = min(mnx, xa[u] + first);
+                mxx = max(mxx, xa[u] + last);
+                mny = min(mny, rr[u]);
+                mxy = max(mxy, rr[u]);
+            }
+        }
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx);
+    mxx = __reduce_max_sync(0xffffffffu, mxx);
+    mny = __reduce_min_sync(0xffffffffu, mny);
+    mxy = __reduce_max_sync(0xffffffffu, mxy);
+    __shared__ int red[kBoxThreads / 32][4];
+    if (lane == 0) { red[warp][0] = mnx; red[warp][1] = mxx; red[warp][2] = mny; red[warp][3] = mxy; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        int v = red[0][threadIdx.x], top = red[0][1];
+#pragma unroll
+        for (int i = 1; i < kBoxThreads / 32; i++) {
+            v = (threadIdx.x & 1) ? max(v, red[i][threadIdx.x]) : min(v, red[i][threadIdx.x]);
+            top = max(top, red[i][1]);
+        }
+        if (top > -0x7fffffff) {                                                  // something changed inside the slab
+            int *dst = reinterpret_cast<int *>(a.boxes + (size_t)f * a.n_obj + k) + threadIdx.x;
+            if (threadIdx.x & 1) atomicMax(dst, v);
+            else atomicMin(dst, v);
+        }
+    }
+}
+
+int launch_box_windows(const KArgs &a, int total_frames, cudaStream_t st)
+{
+    int launches = 0;
+    for (int f0 = 0; f0 < total_frames; f0 += 65535) {
+        const int nf = total_frames - f0 < 65535 ? total_frames - f0 : 65535;
+        KArgs b = a;
+        b.f_base = f0;
+        k_box_windows<<<dim3(kBoxSlabs, a.n_obj, nf), kBoxThreads, 0, st>>>(b);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return -(int)e;
+        launches++;
+    }
+    return launches;
+}
+
 // ---- order of the six loads of the fused kernels --------------------------------------------------------------------------
 // Measured on three B200 boards (profiles/r02_ab_kernel_variants.txt, "load order"): chroma loads issued early are 1.5 % faster
 // at 1080p and 1.7 - 2 % at 720p on every board; at 4K the same order is bimodal (213 us or 235 - 245 us from one round of 30
@@ -589,9 +692,17 @@ int launch_step(const StepArgs &s, cudaStream_t st)
         if (a.mb_map) b.mb_map = a.mb_map + f0 * mbs;
         if (a.summary) b.summary = a.summary + 2 * f0;
         if (a.boxes) { b.windows = a.windows + f0 * s.n_obj; b.boxes = a.boxes + f0 * s.n_obj; }
-        const int r = s.bgr ? launch_tile<true, true>(b, ns * s.n_frames, st) : launch_tile<false, true>(b, ns * s.n_frames, st);
+        KArgs step = b;
+        if (s.box_windowed) step.boxes = nullptr;          // the plain step; the boxes come from the pass over the windows
+        const int r = s.bgr ? launch_tile<true, true>(step, ns * s.n_frames, st) : launch_tile<false, true>(step, ns * s.n_frames, st);
         if (r < 0) return r;
         launches += r;
+        if (a.boxes && s.box_windowed) {
+            b.nf_magic = b.n_frames > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)b.n_frames - 1) / (uint64_t)b.n_frames) : 0u;
+            const int rb = launch_box_windows(b, ns * s.n_frames, st);
+            if (rb < 0) return rb;
+            launches += rb;
+        }
     }
     return launches;
 }

@@ -51,6 +51,7 @@ struct StepArgs {
     const int *windows;       // n_obj x {x0, x1, y0, y1} per frame, inclusive, 16-byte aligned
     int *boxes;               // n_obj x {min_x, max_x, min_y, max_y} per frame, 16-byte aligned
     int n_obj;                // 1 .. 16
+    int box_windowed;         // 1: plain fused step + a pass over the windows only (k_box_windows) instead of the fused box
     PicLayout pic;            // pic.pic16 != NULL: the frames are decoder pictures (i420 unused, bgr mandatory, no boxes)
 };
 

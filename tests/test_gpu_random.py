@@ -144,21 +144,25 @@ def test_random_fused_box(lv, orc, torch_cuda, seed):
             ya, yb = sorted(int(v) for v in rng.integers(0, h, 2))
             wins[f, j] = (xa, xb, ya, yb)
     wins[0, 0] = (0, w - 1, 0, h - 1)
-    ctx = lv.Context(w, h, ns, tol, 0)
-    for s in range(ns):
-        ctx.set_prev_luma(s, state[s])
-    out = ctx.alloc_outputs(n)
-    boxes = ctx.convert_diff_box_batch(torch.from_numpy(frames.reshape(-1)).cuda(), ns, nf, out, torch.from_numpy(wins).cuda())
-    torch.cuda.synchronize()
     want = np.zeros((n, k, 4), np.int32)
     for f in range(n):
         for j in range(k):
             want[f, j] = orc.object_box(ref["mask"][f * px:(f + 1) * px], w, *[int(v) for v in wins[f, j]])
-    assert np.array_equal(boxes.cpu().numpy(), want), (w, h, ns, nf, k)
-    assert np.array_equal(out["bgr"].cpu().numpy(), ref["bgr"])
-    assert np.array_equal(out["mb_count"].cpu().numpy().view(np.uint16), ref["mb_count"])
-    assert np.array_equal(out["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2), ref["summary"])
-    ctx.close()
+    for windowed in (False, True):
+        ctx = lv.Context(w, h, ns, tol, 0)
+        for s in range(ns):
+            ctx.set_prev_luma(s, state[s])
+        out = ctx.alloc_outputs(n)
+        boxes = ctx.convert_diff_box_batch(torch.from_numpy(frames.reshape(-1)).cuda(), ns, nf, out, torch.from_numpy(wins).cuda(),
+                                           windowed=windowed)
+        torch.cuda.synchronize()
+        assert np.array_equal(boxes.cpu().numpy(), want), (w, h, ns, nf, k, windowed)
+        assert np.array_equal(out["bgr"].cpu().numpy(), ref["bgr"])
+        assert np.array_equal(out["mb_count"].cpu().numpy().view(np.uint16), ref["mb_count"])
+        assert np.array_equal(out["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2), ref["summary"])
+        for s in range(ns):
+            assert np.array_equal(ctx.get_prev_luma(s), prev[s]), (windowed, s)
+        ctx.close()
 
 
 # ---- decoder pictures (16-bit planes, crop) into the fused kernel and through the narrowing kernel ---------------------

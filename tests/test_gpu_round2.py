@@ -46,7 +46,7 @@ def _oracle_boxes(orc, mask, w, h, wins):
 
 
 @pytest.mark.parametrize("w,h,ns,nf,k", [(352, 288, 2, 3, 1), (1280, 720, 1, 2, 3), (1920, 1080, 1, 2, 16), (64, 48, 3, 2, 2),
-                                         (720, 576, 1, 2, 2)])
+                                         (720, 576, 1, 2, 2), (32752, 64, 1, 2, 2), (16, 4096, 1, 2, 3)])
 def test_fused_box_matches_reference_scan(lv, orc, torch_cuda, w, h, ns, nf, k):
     """Boxes from the fused launch == lvo_object_box on the mask the same launch would have written; every other output
     of the step is unchanged; no mask buffer is allocated."""
@@ -66,19 +66,20 @@ def test_fused_box_matches_reference_scan(lv, orc, torch_cuda, w, h, ns, nf, k):
     wins[-1, -1] = (5, 5, 7, 7)                          # a single pixel
     if n > 1:
         wins[1, 0] = (w - 1, w - 1, 0, h - 1)            # the last column
-    ctx = lv.Context(w, h, ns, 20, 0)
     d_in = torch.from_numpy(frames.reshape(-1)).cuda()
-    out = ctx.alloc_outputs(n)
-    boxes = ctx.convert_diff_box_batch(d_in, ns, nf, out, torch.from_numpy(wins).cuda())
-    torch.cuda.synchronize()
-    assert np.array_equal(boxes.cpu().numpy(), _oracle_boxes(orc, ref["mask"], w, h, wins))
-    assert np.array_equal(out["bgr"].cpu().numpy(), ref["bgr"])
-    assert np.array_equal(out["mb_count"].cpu().numpy().view(np.uint16), ref["mb_count"])
-    assert np.array_equal(out["mb_map"].cpu().numpy(), ref["mb_map"])
-    assert np.array_equal(out["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2), ref["summary"])
-    for s in range(ns):
-        assert np.array_equal(ctx.get_prev_luma(s), prev[s])
-    ctx.close()
+    for windowed in (False, True):            # the fused box, and LV_BOX_WINDOWED: plain step + a pass over the windows
+        ctx = lv.Context(w, h, ns, 20, 0)
+        out = ctx.alloc_outputs(n)
+        boxes = ctx.convert_diff_box_batch(d_in, ns, nf, out, torch.from_numpy(wins).cuda(), windowed=windowed)
+        torch.cuda.synchronize()
+        assert np.array_equal(boxes.cpu().numpy(), _oracle_boxes(orc, ref["mask"], w, h, wins)), windowed
+        assert np.array_equal(out["bgr"].cpu().numpy(), ref["bgr"])
+        assert np.array_equal(out["mb_count"].cpu().numpy().view(np.uint16), ref["mb_count"])
+        assert np.array_equal(out["mb_map"].cpu().numpy(), ref["mb_map"])
+        assert np.array_equal(out["summary"].cpu().numpy().view(np.uint32).reshape(-1, 2), ref["summary"])
+        for s in range(ns):
+            assert np.array_equal(ctx.get_prev_luma(s), prev[s])
+        ctx.close()
 
 
 def test_fused_box_empty_windows_and_static_background_loop(lv, orc, torch_cuda):
@@ -103,6 +104,10 @@ def test_fused_box_empty_windows_and_static_background_loop(lv, orc, torch_cuda)
     wins = ctx.object_windows(d_obj)
     out = ctx.alloc_outputs(nf, bgr=False)
     boxes = ctx.convert_diff_box_batch(torch.from_numpy(frames.reshape(-1)).cuda(), 1, nf, out, wins)
+    # the same step with the boxes from the pass over the windows (static reference, no BGR): identical boxes
+    boxes_w = ctx.convert_diff_box_batch(torch.from_numpy(frames.reshape(-1)).cuda(), 1, nf, ctx.alloc_outputs(nf, bgr=False), wins,
+                                         windowed=True)
+    assert torch.equal(boxes, boxes_w)
     ctx.object_update(boxes, d_obj)
     torch.cuda.synchronize()
     # oracle: the reference's loops

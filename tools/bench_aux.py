@@ -62,6 +62,9 @@ def main():
         boxes = torch.empty((n, n_obj, 4), dtype=torch.int32, device="cuda")
         row(f"fused + object box ({tag})", timeit(lambda: ctx.convert_diff_box_batch(d_in, 1, n, lean, d_w, boxes)), 5.5,
             note="no mask in memory; init kernel in place of the summary memset")
+        row(f"plain step + box pass over the windows ({tag})",
+            timeit(lambda: ctx.convert_diff_box_batch(d_in, 1, n, lean, d_w, boxes, windowed=True)), 5.5,
+            note="LV_BOX_WINDOWED: init kernel + plain fused kernel + k_box_windows")
     row("convert only (K2)", timeit(lambda: ctx.convert_batch(d_in, n, out["bgr"])), 4.5)
     # difference only over explicit planes: cur = luma planes of the batch, ref = the same shifted by one frame
     ys = torch.stack([d_in[f * ctx.frame_bytes: f * ctx.frame_bytes + px] for f in range(n)]).reshape(-1).contiguous()
