@@ -11,7 +11,7 @@ LIB   := livevideo_b200/liblivevideo.so
 all: $(LIB)
 
 $(LIB): $(DEPS)
-	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared -Xcompiler -fPIC,-fvisibility=hidden \
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -DLV_BUILDING_LIBRARY -shared -Xcompiler -fPIC,-fvisibility=hidden \
 	    -Xptxas -O3 -cudart shared -ldl -o $@ $(SRCS)
 
 oracle:

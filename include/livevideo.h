@@ -27,8 +27,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#if defined(_WIN32)
+#if defined(_WIN32)                 /* the reference is a Win32 application: the library is a DLL there */
+#ifdef LV_BUILDING_LIBRARY
 #define LV_API __declspec(dllexport)
+#else
+#define LV_API __declspec(dllimport)
+#endif
 #else
 #define LV_API __attribute__((visibility("default")))
 #endif

@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into livevideo_b200/liblivevideo.so."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [nvcc_path(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    cmd = [nvcc_path(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-DLV_BUILDING_LIBRARY", "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
            "-Xptxas", "-v" if verbose else "-O3", "-cudart", "shared", "-ldl", "-o", LIB_PATH] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
