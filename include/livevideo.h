@@ -281,6 +281,14 @@ LV_API int lv_host_free(void *p);
  * by DMA instead of through the driver's pageable staging.  Keep the range allocated until lv_host_unregister. */
 LV_API int lv_host_register(void *p, size_t bytes);
 LV_API int lv_host_unregister(void *p);
+/* 1 when [p, p + bytes) lies in a range pinned AND mapped through this library, i.e. the legacy entries take the zero-copy path
+ * for it; 0 otherwise (pageable, or pinned elsewhere).
+ * Environment LV_AUTO_PIN=1 (opt-in, read once): the legacy entries YV12_to_RGB24 / FrameDiff_MB register, in place, every
+ * buffer they see for the second time with the same address and size -- the effect of one lv_host_register per buffer for an
+ * application that is relinked without a source change (1080p: 589 -> 188 us per YV12_to_RGB24 call from the third call on).
+ * Only for applications that keep their buffers for their lifetime, as the reference does (MainDlg.cpp:39-51): a range stays
+ * registered until the process ends. */
+LV_API int lv_host_is_mapped(const void *p, size_t bytes);
 /* How lv_step_host / lv_step_host_pictures would cut a step of n_streams x n_frames frames into chunks under the current
  * environment, without touching a device (pure host logic; the CPU tests walk it): returns the number of chunks and stores
  * up to max_chunks of them as {first stream, streams, first frame, frames} in chunks4.  in_frame_bytes = host bytes per

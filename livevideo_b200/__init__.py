@@ -5,7 +5,7 @@ and `api.py`, the host-side mirror of the reference interface.  Importing the pa
 CUDA; the first call does, and fails loudly when liblivevideo.so or a device is missing.
 """
 from .api import (DEFAULT_MB_THRESH, DEFAULT_TOL, ColorSpaceConversions, Context, FrameDiff_MB, FrameDiff_MB_multi,  # noqa: F401
-                  gen_synthetic, get_kernel_variant, get_zero_copy, host_register, host_step_plan, host_unregister, pinned,
+                  gen_synthetic, get_kernel_variant, get_zero_copy, host_is_mapped, host_register, host_step_plan, host_unregister, pinned,
                   set_kernel_variant,
                   set_zero_copy)
 from .capi import LiveVideoError, lib, lib_path  # noqa: F401

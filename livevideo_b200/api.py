@@ -495,6 +495,11 @@ def host_register(a):
     capi.check(capi.lib().lv_host_register(a.ctypes.data, a.nbytes), "lv_host_register")
 
 
+def host_is_mapped(a):
+    """True when the numpy array lies in memory pinned and mapped through this library (the legacy entries' zero-copy path)."""
+    return bool(capi.lib().lv_host_is_mapped(a.ctypes.data, a.nbytes))
+
+
 def host_unregister(a):
     capi.check(capi.lib().lv_host_unregister(a.ctypes.data), "lv_host_unregister")
 

@@ -61,6 +61,7 @@ SYMBOLS = {
     "lv_host_free": (C.c_int, [_vp]),
     "lv_host_register": (C.c_int, [_vp, C.c_size_t]),
     "lv_host_unregister": (C.c_int, [_vp]),
+    "lv_host_is_mapped": (C.c_int, [_vp, C.c_size_t]),
     "lv_host_step_plan": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, _vp, C.c_int]),
     "lv_step_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "lv_step_host_pictures": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp,

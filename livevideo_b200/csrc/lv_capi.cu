@@ -152,6 +152,42 @@ uint8_t *mapped(const void *p, size_t n)
     return nullptr;
 }
 
+// LV_AUTO_PIN=1 (opt-in): the legacy entries pin + map, in place, every buffer they are handed for the SECOND time with the same
+// address and size -- what a maintainer would do with one lv_host_register() per buffer after its malloc, for an application
+// that is relinked without touching its source.  The reference allocates its planes and its RGB buffer once per dialog and
+// keeps them (MainDlg.cpp:39-51), which is the only pattern this is safe for: a range stays registered until the process
+// ends, so memory that is freed and handed out again by the allocator must not come through here.
+struct SeenBuffer {
+    uintptr_t p;
+    size_t n;
+    int count;
+};
+std::mutex g_seen_mu;
+std::vector<SeenBuffer> g_seen;
+void auto_pin(const void *p, size_t n)
+{
+    static const bool on = [] { const char *e = getenv("LV_AUTO_PIN"); return e && e[0] == '1'; }();
+    if (!on || !p || !n || mapped(p, n)) return;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    {
+        std::lock_guard<std::mutex> lk(g_seen_mu);
+        SeenBuffer *hit = nullptr;
+        for (SeenBuffer &b : g_seen)
+            if (b.p == a) { hit = &b; break; }
+        if (!hit) {
+            if (g_seen.size() >= 256) g_seen.erase(g_seen.begin());
+            g_seen.push_back({a, n, 1});
+            return;
+        }
+        if (hit->n != n) { hit->n = n; hit->count = 1; return; }
+        if (++hit->count != 2) return;                 // pin on the second sighting; one attempt per buffer
+    }
+    if (cudaHostRegister(const_cast<void *>(p), n, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess)
+        pinned_add(const_cast<void *>(p), n);
+    else
+        cudaGetLastError();                             // e.g. a page shared with a range already registered: stays pageable
+}
+
 // 0 = never address host memory from a kernel (always stage through device buffers), 1 = zero-copy with the tile
 // kernel's store pattern, 2 = zero-copy with link-friendly stores (default).  LV_ZEROCOPY sets the initial value.
 int g_zero_copy = -1;
@@ -739,6 +775,8 @@ int lv_host_register(void *p, size_t bytes)
     return LV_OK;
 }
 
+int lv_host_is_mapped(const void *p, size_t bytes) { return p && bytes && mapped(p, bytes) ? 1 : 0; }
+
 int lv_host_unregister(void *p)
 {
     if (!p) return LV_OK;
@@ -1077,6 +1115,7 @@ void YV12_to_RGB24(unsigned char *src0, unsigned char *src1, unsigned char *src2
     LegacyScope scope(fn);
     cudaStream_t st = scope.st;
     const size_t px = (size_t)width * height;
+    auto_pin(src0, px); auto_pin(src1, px / 4); auto_pin(src2, px / 4); auto_pin(dst_ori, 3 * px);
     if (zero_copy_mode() && geom_fast(width, height)) {
         // all four buffers pinned + mapped in place: one kernel reads the planes and writes the picture over the link
         lv::PlaneTable t{};
@@ -1147,6 +1186,10 @@ void FrameDiff_MB(const unsigned char *cur_y, const unsigned char *ref_y, int wi
     const size_t px = (size_t)width * height;
     const int mb_w = (width + 15) / 16, mb_h = (height + 15) / 16;
     const size_t mbs = (size_t)mb_w * mb_h;
+    auto_pin(cur_y, px); auto_pin(ref_y, px);
+    if (mask) auto_pin(mask, px);
+    if (mb_count) auto_pin(mb_count, 2 * mbs);
+    if (mb_map) auto_pin(mb_map, mbs);
     if (zero_copy_mode() && geom_fast(width, height) && tol >= 0 && lv::kernel_variant() != 1) {
         // the planes (and the byte mask) pinned + mapped in place: the difference kernel addresses them directly; the two
         // small per-macroblock outputs go the same way when they are mapped too, else through the device scratch

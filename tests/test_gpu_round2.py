@@ -620,3 +620,52 @@ def test_randomized_geometry_batch_and_threshold_sweep(lv, orc, torch_cuda, seed
     for s_ in range(ns):
         assert np.array_equal(ctx.get_prev_luma(s_), prev[s_])
     ctx.close()
+
+
+# ---- LV_AUTO_PIN: a relinked application that never calls lv_host_register -----------------------------------------------
+def test_auto_pin_registers_buffers_seen_twice(orc, torch_cuda, tmp_path):
+    """LV_AUTO_PIN=1 (read once per process: the case runs in a child): plain malloc'ed planes handed to YV12_to_RGB24 /
+    FrameDiff_MB are pageable on the first two calls and pinned + mapped from then on (zero-copy path); every call returns the
+    oracle's bytes; a buffer seen with another size is not registered on that call; without the variable nothing is pinned."""
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import livevideo_b200 as lv, lvoracle as orc
+w, h = 640, 360
+px = w * h
+rng = np.random.default_rng(3)
+fr = rng.integers(0, 256, px * 3 // 2, dtype=np.uint8)
+y, u, v = fr[:px].copy(), fr[px:px + px // 4].copy(), fr[px + px // 4:].copy()
+dst = np.zeros(3 * px, np.uint8)
+ref = np.roll(y, 5)
+want = orc.convert_frame(fr, w, h)
+wm, wc, wb, _ = orc.frame_diff_mb(y, ref, w, h, 20, 0)
+csc = lv.ColorSpaceConversions()
+states = []
+mask, cnt, mp = np.zeros(px, np.uint8), np.zeros(((w + 15) // 16) * ((h + 15) // 16), np.uint16), np.zeros(((w + 15) // 16) * ((h + 15) // 16), np.uint8)
+for call in range(4):
+    dst[:] = 0
+    csc.YV12_to_RGB24(y, u, v, dst, w, h)
+    assert np.array_equal(dst, want), call
+    lv.FrameDiff_MB(y, ref, w, h, 20, 0, mask=mask, mb_count=cnt, mb_map=mp)
+    assert np.array_equal(mask, wm) and np.array_equal(cnt, wc) and np.array_equal(mp, wb), call
+    states.append((lv.host_is_mapped(y), lv.host_is_mapped(dst), lv.host_is_mapped(ref), lv.host_is_mapped(mask)))
+print("STATES", states)
+'''
+    import subprocess
+    root = ROOT
+    script = tmp_path / "autopin.py"
+    script.write_text(code % (root, os.path.join(root, "oracle")))
+    env = dict(os.environ, LV_AUTO_PIN="1")
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("STATES")][0]
+    states = eval(line[len("STATES "):])
+    # y goes through both entries, so it has been seen twice after the first round; the others after the second
+    assert states[0] == (True, False, False, False), states
+    assert all(states[1]) and all(states[3]), states
+    env.pop("LV_AUTO_PIN")
+    r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("STATES")][0]
+    assert not any(any(s) for s in eval(line[len("STATES "):]))
